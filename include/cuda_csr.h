@@ -1,0 +1,52 @@
+/* cuda_csr.h -- GPU CSR SpMV entry points exported by libspmv_b200.
+ *
+ * These seven symbols are exactly what the reference's host code binds
+ * (reference include/cuda_csr.h:10-25; callers src/csr.c:382-415).  Contract
+ * kept from the reference launchers (src/cuda_csr.cu:210-371):
+ *   - A, x (length A->N) and y (length A->M) are HOST pointers owned by the
+ *     caller; nothing is retained beyond an internal device-side cache;
+ *   - y is fully written when the call returns (synchronous);
+ *   - the return value is the elapsed time of the SpMV kernel(s) only, in
+ *     milliseconds (transfers excluded);
+ *   - set_csr_warps_per_block() selects the CTA size (32*wppb threads) used by
+ *     the next call from the same thread.
+ * Difference: every CUDA call is checked; on failure a line is printed to
+ * stderr and a value <= 0 is returned (=> compute_gflops() == 0).
+ *
+ * Which sm_100a kernel sits behind each entry (the CSV `kernel` id keeps its
+ * position, reference src/main.c:259-263):
+ *   0 csr_spmv_cuda_thread_row        one thread per row
+ *   1 csr_spmv_cuda_warp_row          one warp per row, shuffle reduction
+ *   2 csr_spmv_cuda_halfwarp_row      ADAPTIVE: rows binned by length into
+ *                                     sub-warp / warp / block-per-row groups
+ *   3 csr_spmv_cuda_block_row         one CTA per row
+ *   4 csr_spmv_cuda_halfwarp_row_text STREAM: value/index streams staged in
+ *                                     shared memory by cp.async.bulk (TMA)
+ */
+#ifndef SPMV_B200_CUDA_CSR_H
+#define SPMV_B200_CUDA_CSR_H
+
+#include "csr.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+void set_csr_warps_per_block(int wppb);
+
+double csr_spmv_cuda_thread_row(const sparse_csr *A, const double *x, double *y,
+                                void *_unused);
+double csr_spmv_cuda_warp_row(const sparse_csr *A, const double *x, double *y,
+                              void *_unused);
+double csr_spmv_cuda_halfwarp_row(const sparse_csr *A, const double *x,
+                                  double *y, void *_unused);
+double csr_spmv_cuda_block_row(const sparse_csr *A, const double *x, double *y,
+                               void *_unused);
+double csr_spmv_cuda_halfwarp_row_text(const sparse_csr *A, const double *x,
+                                       double *y, void *_unused);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* SPMV_B200_CUDA_CSR_H */

@@ -1,0 +1,46 @@
+/* cuda_hll.h -- GPU HLL SpMV entry points exported by libspmv_b200.
+ *
+ * Same five symbols as the reference (include/cuda_hll.h:10-22; callers
+ * src/hll.c:226-256).  H, x, y are HOST pointers; the host layout of H is the
+ * one the entry point implies (row-major for _threads_row_major and
+ * _halfwarp_row, column-major for _threads_col_major and _warp_block,
+ * reference src/main.c:324-325) and its padding is JA = -1 / AS = 0.0.  On
+ * upload the library flattens all hacks into ONE value buffer and ONE index
+ * buffer, column-major per hack with a fixed stride of 32 rows, and rewrites
+ * each -1 to the previous valid column of the row (0 for an empty row) --
+ * the same branch-free device convention as reference src/cuda_hll.cu:173-195.
+ * Return value: kernel milliseconds; <= 0 on error.
+ *
+ * CSV `kernel` ids (reference src/main.c:310-315):
+ *   0 hll_spmv_cuda_threads_row_major  thread per row, scalar loads
+ *                                      (row-major input transposed on upload)
+ *   1 hll_spmv_cuda_threads_col_major  thread per row, scalar loads
+ *   2 hll_spmv_cuda_warp_block         warp per hack, 128-bit vector loads
+ *   3 hll_spmv_cuda_halfwarp_row       warp per hack, streams staged in shared
+ *                                      memory by cp.async.bulk (TMA)
+ */
+#ifndef SPMV_B200_CUDA_HLL_H
+#define SPMV_B200_CUDA_HLL_H
+
+#include "hll.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+void set_hll_warps_per_block(int wppb);
+
+double hll_spmv_cuda_threads_row_major(const sparse_hll *H, const double *x,
+                                       double *y, void *_unused);
+double hll_spmv_cuda_threads_col_major(const sparse_hll *H, const double *x,
+                                       double *y, void *_unused);
+double hll_spmv_cuda_warp_block(const sparse_hll *H, const double *x, double *y,
+                                void *_unused);
+double hll_spmv_cuda_halfwarp_row(const sparse_hll *H, const double *x,
+                                  double *y, void *_unused);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* SPMV_B200_CUDA_HLL_H */

@@ -1,0 +1,416 @@
+"""TEST INFRASTRUCTURE -- Python face of the oracle.  Not product code.
+
+Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl
+reference) may import this module; nothing under spmv_scpa_b200/ does.
+
+Two checkers live here:
+
+  port  liboracle.so, the plain-C restatement in oracle.c (always available
+        once built; strict IEEE, serial unless stated);
+  ref   oracle/_ref/libspmv_ref_host*.so, the reference's OWN host sources
+        (src/{mmio,utils,vector,logger,csr,hll}.c) compiled unmodified by
+        oracle/Makefile with the reference's flags.  Built only where
+        /root/reference exists; the prebuilt file travels to the GPU box.
+
+The ctypes structs below restate the reference ABI (include/csr.h:7-13,
+include/hll.h:13-37, include/utils.h:32-47, include/vector.h:6-9) on their
+own so the oracle does not depend on the product package.
+"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+HACK = 32
+
+_ip = C.POINTER(C.c_int)
+_dp = C.POINTER(C.c_double)
+_i64p = C.POINTER(C.c_int64)
+
+
+def _ci(a):
+    return a.ctypes.data_as(_ip)
+
+
+def _cd(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _ci64(a):
+    return a.ctypes.data_as(_i64p)
+
+
+def aligned(n, dtype):
+    """64-byte aligned array (the reference's OpenMP path asserts it, src/csr.c:309-311)."""
+    item = np.dtype(dtype).itemsize
+    raw = np.zeros(n * item + 64, dtype=np.uint8)
+    shift = (-raw.ctypes.data) % 64
+    return raw[shift:shift + n * item].view(dtype)
+
+
+def aligned_copy(a, dtype):
+    out = aligned(len(a), dtype)
+    out[:] = a
+    return out
+
+
+# ------------------------------------------------------------------ the port --
+_port = None
+
+
+def port():
+    global _port
+    if _port is None:
+        path = os.path.join(HERE, "liboracle.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"{path} missing: run `make -C oracle`")
+        lib = C.CDLL(path)
+        lib.orc_load_mtx.restype = C.c_int
+        lib.orc_load_mtx.argtypes = [C.c_char_p, _ip, _ip, _ip, C.POINTER(_ip), C.POINTER(_ip),
+                                     C.POINTER(_dp)]
+        lib.orc_free.argtypes = [C.c_void_p]
+        lib.orc_hll_shape.restype = C.c_int64
+        lib.orc_hll_shape.argtypes = [C.c_int, _ip, _ip, _ip, _ip, _i64p]
+        lib.orc_hll_pack.argtypes = [C.c_int, _ip, _ip, _dp, C.c_int, _i64p, _ip, _dp]
+        lib.orc_hll_patch_pads.argtypes = [C.c_int, _ip, _ip, _i64p, C.c_int, _ip]
+        lib.orc_csr_spmv.argtypes = [C.c_int, _ip, _ip, _dp, _dp, _dp]
+        lib.orc_csr_spmv64.argtypes = [C.c_int64, _i64p, _ip, _dp, _dp, _dp]
+        lib.orc_csr_abs_bound.argtypes = [C.c_int, _ip, _ip, _dp, _dp, _dp]
+        lib.orc_hll_spmv.argtypes = [C.c_int, _ip, _ip, _i64p, C.c_int, _ip, _dp, _dp, _dp]
+        lib.orc_partition_rows.restype = C.c_int
+        lib.orc_partition_rows.argtypes = [C.c_int, _ip, C.c_int, _ip]
+        lib.orc_csr_spmv_timed.restype = C.c_double
+        lib.orc_csr_spmv_timed.argtypes = [C.c_int, _ip, _ip, _dp, _dp, _dp, C.c_int]
+        lib.orc_max_threads.restype = C.c_int
+        _port = lib
+    return _port
+
+
+def load_mtx(path):
+    """(M, N, IRP, JA, AS) following reference src/csr.c:31-171; OSError(errno) on failure."""
+    M, N, NZ = C.c_int(), C.c_int(), C.c_int()
+    irp, ja, as_ = _ip(), _ip(), _dp()
+    rc = port().orc_load_mtx(os.fsencode(path), C.byref(M), C.byref(N), C.byref(NZ), C.byref(irp),
+                             C.byref(ja), C.byref(as_))
+    if rc:
+        raise OSError(-rc, os.strerror(-rc))
+    IRP = np.ctypeslib.as_array(irp, shape=(M.value + 1,)).copy()
+    JA = np.ctypeslib.as_array(ja, shape=(max(NZ.value, 1),))[:NZ.value].copy()
+    AS = np.ctypeslib.as_array(as_, shape=(max(NZ.value, 1),))[:NZ.value].copy()
+    for p in (irp, ja, as_):
+        port().orc_free(C.cast(p, C.c_void_p))
+    return M.value, N.value, IRP, JA, AS
+
+
+def csr_to_hll(M, IRP, JA, AS, col_major):
+    """rows, width, nz, off, ja, as  (reference src/hll.c:19-95)."""
+    nb = (M + HACK - 1) // HACK
+    IRP = np.ascontiguousarray(IRP, np.int32)
+    JA = np.ascontiguousarray(JA, np.int32)
+    AS = np.ascontiguousarray(AS, np.float64)
+    rows = np.zeros(nb, np.int32)
+    width = np.zeros(nb, np.int32)
+    nz = np.zeros(nb, np.int32)
+    off = np.zeros(nb + 1, np.int64)
+    slots = port().orc_hll_shape(M, _ci(IRP), _ci(rows), _ci(width), _ci(nz), _ci64(off))
+    ja = np.zeros(slots, np.int32)
+    as_ = np.zeros(slots, np.float64)
+    port().orc_hll_pack(M, _ci(IRP), _ci(JA), _cd(AS), int(bool(col_major)), _ci64(off), _ci(ja),
+                        _cd(as_))
+    return rows, width, nz, off, ja, as_
+
+
+def hll_patch_pads(rows, width, off, col_major, ja):
+    """Device padding convention (reference src/cuda_hll.cu:173-195), returns a patched copy."""
+    out = np.ascontiguousarray(ja, np.int32).copy()
+    port().orc_hll_patch_pads(len(rows), _ci(rows), _ci(width), _ci64(off), int(bool(col_major)),
+                              _ci(out))
+    return out
+
+
+def hll_device_layout(M, IRP, JA, AS):
+    """What libspmv_b200 must hold in HBM for this matrix (include/cuda_hll.h): per hack,
+    column-major with stride 32, pads patched, rows beyond M all pads.
+    Returns hoff[nb+1], ja[slots32], as[slots32]."""
+    rows, width, nz, off, ja, as_ = csr_to_hll(M, IRP, JA, AS, True)
+    ja = hll_patch_pads(rows, width, off, True, ja)
+    nb = len(rows)
+    hoff = np.zeros(nb + 1, np.int64)
+    hoff[1:] = np.cumsum(32 * width.astype(np.int64))
+    dja = np.zeros(hoff[-1], np.int32)
+    das = np.zeros(hoff[-1], np.float64)
+    for b in range(nb):
+        r, w = int(rows[b]), int(width[b])
+        if w == 0:
+            continue
+        src_j = ja[off[b]:off[b + 1]].reshape(w, r)
+        src_a = as_[off[b]:off[b + 1]].reshape(w, r)
+        dst_j = dja[hoff[b]:hoff[b + 1]].reshape(w, 32)
+        dst_a = das[hoff[b]:hoff[b + 1]].reshape(w, 32)
+        dst_j[:, :r] = src_j
+        dst_a[:, :r] = src_a
+    return hoff, dja, das
+
+
+def csr_spmv(M, IRP, JA, AS, x):
+    """y = A x, strict left-to-right FP64 (reference src/csr.c:201-216)."""
+    IRP = np.ascontiguousarray(IRP)
+    JA = np.ascontiguousarray(JA, np.int32)
+    AS = np.ascontiguousarray(AS, np.float64)
+    x = np.ascontiguousarray(x, np.float64)
+    y = np.zeros(M, np.float64)
+    if IRP.dtype == np.int64:
+        port().orc_csr_spmv64(M, _ci64(IRP), _ci(JA), _cd(AS), _cd(x), _cd(y))
+    else:
+        IRP = IRP.astype(np.int32, copy=False)
+        port().orc_csr_spmv(M, _ci(IRP), _ci(JA), _cd(AS), _cd(x), _cd(y))
+    return y
+
+
+def csr_abs_bound(M, IRP, JA, AS, x):
+    """bound_i = sum_j |a_ij x_j| (scale of the north-star tolerance)."""
+    IRP = np.ascontiguousarray(IRP)
+    if IRP.dtype == np.int64:
+        # numpy path for 64-bit offsets (tests only use it on small shards)
+        prod = np.abs(np.asarray(AS) * np.asarray(x)[np.asarray(JA)])
+        cs = np.concatenate([[0.0], np.cumsum(prod)])
+        return cs[IRP[1:]] - cs[IRP[:-1]]
+    IRP = IRP.astype(np.int32, copy=False)
+    JA = np.ascontiguousarray(JA, np.int32)
+    AS = np.ascontiguousarray(AS, np.float64)
+    x = np.ascontiguousarray(x, np.float64)
+    b = np.zeros(M, np.float64)
+    port().orc_csr_abs_bound(M, _ci(IRP), _ci(JA), _cd(AS), _cd(x), _cd(b))
+    return b
+
+
+def hll_spmv(M, rows, width, off, col_major, ja, as_, x):
+    x = np.ascontiguousarray(x, np.float64)
+    y = np.zeros(len(rows) * HACK, np.float64)
+    port().orc_hll_spmv(len(rows), _ci(rows), _ci(width), _ci64(off), int(bool(col_major)),
+                        _ci(np.ascontiguousarray(ja, np.int32)),
+                        _cd(np.ascontiguousarray(as_, np.float64)), _cd(x), _cd(y))
+    return y[:M]
+
+
+def partition_rows(M, IRP, parts):
+    IRP = np.ascontiguousarray(IRP, np.int32)
+    cut = np.zeros(parts + 1, np.int32)
+    used = port().orc_partition_rows(M, _ci(IRP), parts, _ci(cut))
+    return cut[:used + 1].copy()
+
+
+def csr_spmv_timed(M, IRP, JA, AS, x, threads=1):
+    """(milliseconds, y) of the port's CSR loop with `threads` OpenMP threads."""
+    y = np.zeros(M, np.float64)
+    ms = port().orc_csr_spmv_timed(M, _ci(IRP), _ci(JA), _cd(AS), _cd(x), _cd(y), threads)
+    return ms, y
+
+
+def max_threads():
+    return port().orc_max_threads()
+
+
+def check_tolerance(y, y_ref, bound, rel=1e-12):
+    """North-star gate: |y_i - y_ref_i| <= rel * sum_j |a_ij x_j| for every row.
+    Returns (ok, worst_ratio) with worst_ratio = max_i |dy_i| / (rel*bound_i)."""
+    y = np.asarray(y, np.float64)
+    y_ref = np.asarray(y_ref, np.float64)
+    err = np.abs(y - y_ref)
+    lim = rel * np.asarray(bound, np.float64)
+    bad = err > lim
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ratio = np.where(lim > 0, err / lim, np.where(err > 0, np.inf, 0.0))
+    worst = float(ratio.max()) if len(ratio) else 0.0
+    return (not bool(bad.any())), worst
+
+
+# ------------------------------------------------------- the reference itself --
+class _vec(C.Structure):
+    _fields_ = [("len", C.c_size_t), ("data", _dp)]
+
+
+class _bench(C.Structure):
+    _fields_ = [("duration_ms", C.c_double), ("gflops", C.c_double), ("data", _vec)]
+
+
+class _bench_omp(C.Structure):
+    _fields_ = [("bench", _bench), ("name", C.c_char * 64), ("num_threads", C.c_int)]
+
+
+class _csr(C.Structure):
+    _fields_ = [("name", C.c_char * 64), ("M", C.c_int), ("N", C.c_int), ("NZ", C.c_int),
+                ("IRP", _ip), ("JA", _ip), ("AS", _dp)]
+
+
+class _blk(C.Structure):
+    _fields_ = [("M", C.c_int), ("N", C.c_int), ("NZ", C.c_int), ("max_NZ", C.c_int), ("JA", _ip),
+                ("AS", _dp)]
+
+
+class _hll(C.Structure):
+    _fields_ = [("name", C.c_char * 64), ("M", C.c_int), ("N", C.c_int), ("NZ", C.c_int),
+                ("hack_size", C.c_int), ("num_blocks", C.c_int), ("blocks", C.POINTER(_blk))]
+
+
+_ref = None
+_ref_kind = None
+
+
+def _native_ok(path):
+    """Run a tiny SpMV through `path` in a child process: a SIGILL (different CPU than
+    the build host) must not take the caller down."""
+    code = ("import ctypes,sys; l=ctypes.CDLL(sys.argv[1]); "
+            "l.aligned_malloc.restype=ctypes.c_void_p; p=l.aligned_malloc(64); print('ok')")
+    try:
+        r = subprocess.run([sys.executable, "-c", code, path], capture_output=True, timeout=60)
+        return r.returncode == 0 and b"ok" in r.stdout
+    except Exception:
+        return False
+
+
+def ref_available():
+    return os.path.exists(os.path.join(HERE, "_ref", "libspmv_ref_host.so"))
+
+
+def ref():
+    """The reference host library (ctypes), or FileNotFoundError."""
+    global _ref, _ref_kind
+    if _ref is None:
+        base = os.path.join(HERE, "_ref", "libspmv_ref_host.so")
+        native = os.path.join(HERE, "_ref", "libspmv_ref_host_native.so")
+        if not os.path.exists(base):
+            raise FileNotFoundError(f"{base} missing: run `make -C oracle` where /root/reference exists")
+        path, _ref_kind = base, "x86-64-v3"
+        if os.environ.get("SPMV_ORACLE_NATIVE", "1") == "1" and os.path.exists(native) and _native_ok(native):
+            path, _ref_kind = native, "native"
+        lib = C.CDLL(path)
+        lib.io_load_csr.restype = C.c_void_p
+        lib.io_load_csr.argtypes = [C.c_char_p]
+        lib.csr_free.argtypes = [C.c_void_p]
+        lib.csr_to_hll.restype = C.c_void_p
+        lib.csr_to_hll.argtypes = [C.POINTER(_csr), C.c_bool]
+        lib.hll_free.argtypes = [C.c_void_p]
+        lib.bench_csr_serial.argtypes = [C.POINTER(_csr), _dp, C.POINTER(_bench)]
+        lib.bench_hll_serial.argtypes = [C.POINTER(_hll), _dp, C.POINTER(_bench)]
+        lib.bench_csr_omp_guided.argtypes = [C.POINTER(_csr), _dp, C.POINTER(_bench_omp)]
+        lib.bench_csr_omp_nnz_balancing.argtypes = [C.POINTER(_csr), _dp, C.POINTER(_bench_omp)]
+        lib.bench_hll_omp.argtypes = [C.POINTER(_hll), _dp, C.POINTER(_bench_omp)]
+        lib.vec_put.argtypes = [C.POINTER(_vec)]
+        lib.vec_create.restype = _vec
+        lib.vec_create.argtypes = [C.c_size_t]
+        lib.vec_fill_random.argtypes = [C.POINTER(_vec)]
+        _ref = lib
+    return _ref
+
+
+def ref_kind():
+    ref()
+    return _ref_kind
+
+
+def _is_err(addr):
+    return addr is None or addr == 0 or addr > (1 << 64) - 4096
+
+
+def ref_load_mtx(path):
+    """The reference's io_load_csr (src/csr.c:31-171) -> (M, N, IRP, JA, AS) copies."""
+    addr = ref().io_load_csr(os.fsencode(path))
+    if _is_err(addr):
+        err = (1 << 64) - addr if addr else 12
+        raise OSError(err, os.strerror(err))
+    A = _csr.from_address(addr)
+    M, N, NZ = A.M, A.N, A.NZ
+    IRP = np.ctypeslib.as_array(A.IRP, shape=(M + 1,)).copy()
+    JA = np.ctypeslib.as_array(A.JA, shape=(max(NZ, 1),))[:NZ].copy()
+    AS = np.ctypeslib.as_array(A.AS, shape=(max(NZ, 1),))[:NZ].copy()
+    name = A.name.decode()
+    ref().csr_free(addr)
+    return M, N, IRP, JA, AS, name
+
+
+class RefCsr:
+    """A sparse_csr for the reference library over aligned copies of numpy arrays."""
+
+    def __init__(self, M, N, IRP, JA, AS, name="m"):
+        self.IRP = aligned_copy(IRP, np.int32)
+        self.JA = aligned_copy(JA, np.int32)
+        self.AS = aligned_copy(AS, np.float64)
+        self.st = _csr()
+        self.st.name = name.encode()[:63]
+        self.st.M, self.st.N, self.st.NZ = M, N, len(JA)
+        self.st.IRP, self.st.JA, self.st.AS = _ci(self.IRP), _ci(self.JA), _cd(self.AS)
+
+    @property
+    def ptr(self):
+        return C.byref(self.st)
+
+
+def ref_csr_to_hll(A: RefCsr, col_major):
+    """The reference's csr_to_hll (src/hll.c:19-95), flattened like csr_to_hll() above."""
+    addr = ref().csr_to_hll(A.ptr, bool(col_major))
+    if _is_err(addr):
+        raise MemoryError("reference csr_to_hll failed")
+    H = _hll.from_address(addr)
+    nb = H.num_blocks
+    rows = np.zeros(nb, np.int32)
+    width = np.zeros(nb, np.int32)
+    nz = np.zeros(nb, np.int32)
+    off = np.zeros(nb + 1, np.int64)
+    ja, as_ = [], []
+    for b in range(nb):
+        blk = H.blocks[b]
+        n = blk.M * blk.max_NZ
+        rows[b], width[b], nz[b] = blk.M, blk.max_NZ, blk.NZ
+        off[b + 1] = off[b] + n
+        if n:
+            ja.append(np.ctypeslib.as_array(blk.JA, shape=(n,)).copy())
+            as_.append(np.ctypeslib.as_array(blk.AS, shape=(n,)).copy())
+    meta = dict(M=H.M, N=H.N, NZ=H.NZ, hack_size=H.hack_size, num_blocks=nb)
+    ref().hll_free(addr)
+    JA = np.concatenate(ja) if ja else np.zeros(0, np.int32)
+    AS = np.concatenate(as_) if as_ else np.zeros(0, np.float64)
+    return rows, width, nz, off, JA, AS, meta
+
+
+def _take(bench):
+    n = bench.data.len
+    y = np.ctypeslib.as_array(bench.data.data, shape=(max(n, 1),))[:n].copy()
+    ref().vec_put(C.byref(bench.data))
+    return y
+
+
+def ref_csr_serial(A: RefCsr, x):
+    """The parity oracle proper: the reference's serial CSR SpMV (src/csr.c:201-216,
+    via bench_csr_serial :342-344).  Returns (ms, y)."""
+    xa = aligned_copy(x, np.float64)
+    b = _bench()
+    rc = ref().bench_csr_serial(A.ptr, _cd(xa), C.byref(b))
+    if rc:
+        raise OSError(-rc, "bench_csr_serial")
+    return b.duration_ms, _take(b)
+
+
+def ref_csr_omp(A: RefCsr, x, threads, schedule="guided"):
+    """Reference OpenMP CSR (src/csr.c:278-339).  The reference asserts
+    threads <= omp_get_max_threads(); the caller must have OMP_NUM_THREADS set accordingly."""
+    xa = aligned_copy(x, np.float64)
+    b = _bench_omp()
+    b.num_threads = threads
+    fn = ref().bench_csr_omp_guided if schedule == "guided" else ref().bench_csr_omp_nnz_balancing
+    rc = fn(A.ptr, _cd(xa), C.byref(b))
+    if rc:
+        raise OSError(-rc, "bench_csr_omp")
+    return b.bench.duration_ms, _take(b.bench), b.num_threads
+
+
+def ref_rand_x(n):
+    """x as the reference makes it: vec_fill_random -> rand()/RAND_MAX (src/vector.c:36-41)."""
+    v = ref().vec_create(n)
+    ref().vec_fill_random(C.byref(v))
+    out = np.ctypeslib.as_array(v.data, shape=(max(n, 1),))[:n].copy()
+    ref().vec_put(C.byref(v))
+    return out

@@ -1,0 +1,203 @@
+// common.cuh -- error plumbing and sm_100a PTX wrappers shared by the kernels.
+//
+// New code (no reference counterpart: the reference checks no CUDA call and
+// uses plain LDG / __ldg only, src/cuda_csr.cu, src/cuda_hll.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libspmv_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace b200 {
+
+// ---------------------------------------------------------------- errors --
+inline char *tls_error() {
+      static thread_local char buf[512];
+      return buf;
+}
+
+inline int fail(int code, const char *fmt, ...) {
+      va_list ap;
+      va_start(ap, fmt);
+      vsnprintf(tls_error(), 512, fmt, ap);
+      va_end(ap);
+      fprintf(stderr, "[ERROR] libspmv_b200: %s\n", tls_error());
+      return code;
+}
+
+#define B200_CUDA(call)                                                        \
+      do {                                                                     \
+            cudaError_t e_ = (call);                                           \
+            if (e_ != cudaSuccess)                                             \
+                  return ::b200::fail(-5 /*EIO*/, "%s failed: %s (%s:%d)",     \
+                                      #call, cudaGetErrorString(e_), __FILE__, \
+                                      __LINE__);                               \
+      } while (0)
+
+#define B200_CUDA_PTR(call)                                                    \
+      do {                                                                     \
+            cudaError_t e_ = (call);                                           \
+            if (e_ != cudaSuccess) {                                           \
+                  ::b200::fail(-5, "%s failed: %s (%s:%d)", #call,             \
+                               cudaGetErrorString(e_), __FILE__, __LINE__);    \
+                  return nullptr;                                              \
+            }                                                                  \
+      } while (0)
+
+constexpr int kWarp = 32;
+constexpr int kHack = 32;
+
+// --------------------------------------------------------- cache policies --
+// L2 eviction priorities are attached per access through a 64-bit policy
+// operand (on sm_100 the bare .L2::evict_* qualifiers are only accepted on
+// 256-bit loads).
+__device__ __forceinline__ uint64_t policy_evict_first() {
+      uint64_t p;
+      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+      return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+      uint64_t p;
+      asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+      return p;
+}
+
+// ------------------------------------------------------- streaming loads --
+// Matrix values / indices are read exactly once per SpMV: keep them out of
+// L1 (no_allocate) and first in line for L2 eviction.
+__device__ __forceinline__ double ld_stream_f64(const double *p, uint64_t pol) {
+      double v;
+      asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;"
+                   : "=d"(v)
+                   : "l"(p), "l"(pol));
+      return v;
+}
+__device__ __forceinline__ int ld_stream_s32(const int *p, uint64_t pol) {
+      int v;
+      asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;"
+                   : "=r"(v)
+                   : "l"(p), "l"(pol));
+      return v;
+}
+__device__ __forceinline__ double2 ld_stream_f64x2(const double *p, uint64_t pol) {
+      double2 v;
+      asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;"
+                   : "=d"(v.x), "=d"(v.y)
+                   : "l"(p), "l"(pol));
+      return v;
+}
+__device__ __forceinline__ int2 ld_stream_s32x2(const int *p, uint64_t pol) {
+      int2 v;
+      asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.s32 {%0,%1}, [%2], %3;"
+                   : "=r"(v.x), "=r"(v.y)
+                   : "l"(p), "l"(pol));
+      return v;
+}
+__device__ __forceinline__ int4 ld_stream_s32x4(const int *p, uint64_t pol) {
+      int4 v;
+      asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;"
+                   : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                   : "l"(p), "l"(pol));
+      return v;
+}
+// 256-bit load (sm_100+): four doubles per lane, 1 KiB per warp instruction.
+struct double4_t {
+      double a, b, c, d;
+};
+__device__ __forceinline__ double4_t ld_stream_f64x4(const double *p) {
+      double4_t v;
+      asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.f64 {%0,%1,%2,%3}, [%4];"
+                   : "=d"(v.a), "=d"(v.b), "=d"(v.c), "=d"(v.d)
+                   : "l"(p));
+      return v;
+}
+
+// ------------------------------------------------------------- x gathers --
+// The irregular gather of x goes through the read-only path, is allowed to
+// live in L1, and is marked evict_last in L2 so the streamed matrix does not
+// push it out.
+__device__ __forceinline__ double ld_x(const double *p, uint64_t pol) {
+      double v;
+      asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;"
+                   : "=d"(v)
+                   : "l"(p), "l"(pol));
+      return v;
+}
+
+// --------------------------------------------------- mbarrier + bulk copy --
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+      return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                   "r"(bytes)
+                   : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+      asm volatile(
+          "{\n"
+          ".reg .pred p;\n"
+          "WAIT_%=:\n"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+          "@p bra DONE_%=;\n"
+          "bra WAIT_%=;\n"
+          "DONE_%=:\n"
+          "}\n" ::"r"(smem_u32(bar)),
+          "r"(parity)
+          : "memory");
+}
+// 1-D bulk copy global -> shared, completion counted in bytes on `bar`.
+// Requirements: src, dst 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src, uint32_t bytes,
+                                         uint64_t *bar, uint64_t pol) {
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+          "[%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst_smem)),
+          "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+          : "memory");
+}
+
+// ------------------------------------------------------------ reductions --
+template <int WIDTH>
+__device__ __forceinline__ double group_sum(double v) {
+#pragma unroll
+      for (int o = WIDTH / 2; o > 0; o >>= 1)
+            v += __shfl_xor_sync(0xffffffffu, v, o, WIDTH);
+      return v;
+}
+
+// Fused epilogue of the multi-GPU halo exchange: rows that a neighbouring
+// rank needs are also stored straight into that rank's halo buffer (peer
+// memory mapped through CUDA IPC, reached over NVLink).
+struct PushArgs {
+      int n;
+      long long row0[2], row1[2];
+      double *dst[2];
+};
+
+__device__ __forceinline__ void store_y(double *y, long long row, double v,
+                                        const PushArgs &push) {
+      y[row] = v;
+      if (push.n) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+                  if (i < push.n && row >= push.row0[i] && row < push.row1[i])
+                        push.dst[i][row - push.row0[i]] = v;
+      }
+}
+
+} // namespace b200

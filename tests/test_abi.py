@@ -1,0 +1,96 @@
+"""The C-ABI libraries load on a CPU-only box and export every symbol include/*.h declares."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+HEADERS_B200 = ["cuda_csr.h", "cuda_hll.h", "cuda_timer.h", "spmv_b200.h"]
+HEADERS_HOST = ["csr.h", "hll.h", "vector.h", "utils.h", "logger.h", "mmio.h", "spmv_gen.h"]
+
+_decl = re.compile(r"^[A-Za-z_][\w\s\*]*?\b(\w+)\s*\(", re.M)
+
+
+def declared_functions(header):
+    text = open(os.path.join(ROOT, "include", header)).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)           # comments
+    text = text.replace("\\\n", " ")                            # join continued lines
+    text = re.sub(r"#\s*define[^\n]*", "", text)                 # macros
+    # drop static inline bodies
+    text = re.sub(r"static\s+inline[^{;]*\{.*?\n\}", "", text, flags=re.S)
+    names = set()
+    for m in re.finditer(r"([\w\*\s]+?)\b(\w+)\s*\(([^;{]*)\)\s*;", text):
+        if m.group(2) not in ("while", "if", "for", "sizeof", "return"):
+            names.add(m.group(2))
+    return sorted(names)
+
+
+def test_struct_sizes(sp):
+    S = sp.structs
+    # reference ABI (sizeof(sparse_csr)=104, ellpack_block=32, sparse_hll=96)
+    assert C.sizeof(S.sparse_csr) == 104
+    assert C.sizeof(S.ellpack_block) == 32
+    assert C.sizeof(S.sparse_hll) == 96
+    assert C.sizeof(S.vec) == 16
+    assert C.sizeof(S.bench) == 32
+    assert C.sizeof(S.bench_cuda) == 40
+    assert C.sizeof(S.cuda_timer) == 16
+
+
+@pytest.mark.parametrize("header", HEADERS_B200)
+def test_libspmv_b200_exports(sp, header):
+    names = declared_functions(header)
+    assert names, header
+    # csr.h/hll.h bench_* live in the host library, not in libspmv_b200
+    for n in names:
+        if n.startswith(("bench_", "io_load", "csr_free", "csr_to_hll", "hll_free", "init_")):
+            continue
+        assert hasattr(sp._lib.b200, n), f"libspmv_b200.so does not export {n} ({header})"
+
+
+@pytest.mark.parametrize("header", HEADERS_HOST)
+def test_libspmv_host_exports(sp, header):
+    for n in declared_functions(header):
+        if n.startswith("init_"):
+            continue  # static inline
+        assert hasattr(sp._lib.host, n), f"libspmv_host.so does not export {n} ({header})"
+
+
+def test_reference_boundary_symbols(sp):
+    """Exactly the 11 names the reference's csr.c / hll.c bind (reference include/cuda_csr.h:10-25,
+    include/cuda_hll.h:10-22)."""
+    want = ["set_csr_warps_per_block", "set_hll_warps_per_block"] + list(
+        sp._lib.CSR_ENTRY_POINTS) + list(sp._lib.HLL_ENTRY_POINTS)
+    assert len(want) == 11
+    for n in want:
+        assert hasattr(sp._lib.b200, n)
+
+
+def test_no_gpu_fails_loudly(sp):
+    """On a box without a GPU the product must refuse, not fall back to a CPU path."""
+    import numpy as np
+    if sp._lib.b200.spmv_b200_device_count() > 0:
+        pytest.skip("GPU present")
+    A = sp.gen_poisson2d(8, 8)
+    with pytest.raises(RuntimeError, match="no CUDA device|CPU path"):
+        sp.bench_csr_cuda_halfwarp_row(A, np.ones(A.N))
+    with pytest.raises(RuntimeError):
+        sp.CsrDevice.from_host(A)
+
+
+def test_product_never_touches_oracle():
+    """Nothing under the product package may import, link or open oracle/."""
+    bad = []
+    for d, _, files in os.walk(os.path.join(ROOT, "spmv_scpa_b200")):
+        for f in files:
+            if f.endswith((".py", ".c", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(d, f), errors="replace").read()
+                for line in txt.splitlines():
+                    s = line.strip()
+                    if ("import" in s or "#include" in s or "CDLL" in s or "dlopen" in s) and "oracle" in s:
+                        bad.append((f, s))
+    assert not bad, bad
+    mk = open(os.path.join(ROOT, "Makefile")).read()
+    assert "liboracle" not in mk.replace("$(MAKE) -C oracle", "")

@@ -1,0 +1,144 @@
+"""PRODUCT host layer vs the reference: loader and packer must be bit-exact.
+
+Checked against the committed reference-run fixtures (tests/golden) and, when
+oracle/_ref is present, against the reference's own code on random inputs.
+Reads like the reference's own call sequence (src/main.c:78-88).
+"""
+import errno
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, GOLDEN_CASES, golden, golden_mtx, random_csr
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float64).view(np.uint64)
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_io_load_csr_bit_exact(sp, case):
+    g = golden(case)
+    A = sp.io_load_csr(golden_mtx(case))
+    assert (A.M, A.N, A.NZ) == (int(g["M"]), int(g["N"]), len(g["JA"]))
+    assert A.name == str(g["name"])
+    assert np.array_equal(A.IRP, g["IRP"])
+    assert np.array_equal(A.JA, g["JA"])
+    assert np.array_equal(bits(A.AS), bits(g["AS"]))
+    for arr in (A.IRP, A.JA, A.AS):
+        if arr.size:
+            assert arr.ctypes.data % 64 == 0  # ALIGNMENT contract (include/utils.h)
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+@pytest.mark.parametrize("layout", ["rm", "cm"])
+def test_csr_to_hll_bit_exact(sp, case, layout):
+    g = golden(case)
+    A = sp.io_load_csr(golden_mtx(case))
+    H = sp.csr_to_hll(A, layout == "cm")
+    assert (H.M, H.N, H.NZ, H.hack_size) == (A.M, A.N, A.NZ, 32)
+    assert H.num_blocks == (A.M + 31) // 32 == len(g[f"{layout}_rows"])
+    rows, width, nz, off, JA, AS = H.flat()
+    assert np.array_equal(rows, g[f"{layout}_rows"])
+    assert np.array_equal(width, g[f"{layout}_width"])
+    assert np.array_equal(nz, g[f"{layout}_nz"])
+    assert np.array_equal(JA, g[f"{layout}_JA"])
+    assert np.array_equal(bits(AS), bits(g[f"{layout}_AS"]))
+    for b in range(H.num_blocks):
+        m, n, _, w, ja, as_ = H.block(b)
+        assert n == A.N
+        if m * w:
+            assert ja.ctypes.data % 64 == 0 and as_.ctypes.data % 64 == 0
+
+
+def test_loader_error_codes(sp):
+    t = np.load(os.path.join(GOLDEN, "load_errors.npz"))
+    for name, want in zip(t["names"], t["errnos"]):
+        with pytest.raises(OSError) as ei:
+            sp.io_load_csr(golden_mtx(str(name)))
+        assert ei.value.errno == int(want), name
+    with pytest.raises(OSError) as ei:
+        sp.io_load_csr("/nonexistent/dir/m.mtx")
+    assert ei.value.errno == errno.ENOENT
+
+
+def test_matrix_name_rule(sp, tmp_path):
+    """basename minus '.mtx', at most 63 chars (reference src/csr.c:18-30)."""
+    body = "%%MatrixMarket matrix coordinate real general\n1 1 1\n1 1 2.0\n"
+    for fname, want in [("abc.mtx", "abc"), ("noext", "noext"), (".mtx", ".mtx"),
+                        ("x" * 80 + ".mtx", "x" * 63), ("a.b.mtx", "a.b")]:
+        p = tmp_path / fname
+        p.write_text(body)
+        assert sp.io_load_csr(str(p)).name == want
+
+
+def test_vec_fill_random_matches_reference_stream(sp):
+    """First 64 draws of a fresh process equal the reference's (golden/rand_x64.npy)."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    code = ("import sys; sys.path.insert(0, %r); import spmv_scpa_b200 as sp; "
+            "sys.stdout.write(sp.vec_fill_random(64).tobytes().hex())" % ROOT)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, check=True).stdout
+    got = np.frombuffer(bytes.fromhex(out.decode()), np.float64)
+    assert np.array_equal(got, np.load(os.path.join(GOLDEN, "rand_x64.npy")))
+
+
+def test_validation_gate(sp):
+    a = np.zeros(10)
+    b = np.zeros(10)
+    b[3] = 0.09
+    assert sp.validation_vec_result(a, b) == 0
+    b[3] = 0.11
+    assert sp.validation_vec_result(a, b) == -1
+    assert sp.validation_vec_result(a, np.zeros(9)) == -1
+
+
+# ---------------------------------------------------------------- live vs _ref --
+def test_product_packer_vs_reference_live(sp, O, have_ref):
+    if not have_ref:
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(3)
+    for trial in range(25):
+        M = int(rng.integers(1, 200))
+        N = int(rng.integers(1, 100))
+        IRP, JA, AS = random_csr(rng, M, N, int(rng.integers(0, 50)), empty_frac=float(rng.random()))
+        A = sp.csr_from_arrays("t", M, N, IRP, JA, AS)
+        R = O.RefCsr(M, N, IRP, JA, AS)
+        for cm in (False, True):
+            want = O.ref_csr_to_hll(R, cm)
+            got = sp.csr_to_hll(A, cm).flat()
+            for w, g_ in zip(want[:5], got[:5]):
+                assert np.array_equal(w, g_)
+            assert np.array_equal(bits(want[5]), bits(got[5]))
+
+
+def test_product_loader_vs_reference_live(sp, O, have_ref, tmp_path):
+    if not have_ref:
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(17)
+    fmts = ["%.17g", "%e", "%.3f", "%g"]
+    for trial, (field, sym) in enumerate([("real", "general"), ("real", "symmetric"),
+                                          ("pattern", "general"), ("pattern", "symmetric"),
+                                          ("real", "skew-symmetric"), ("real", "hermitian")] * 3):
+        M = int(rng.integers(1, 80))
+        N = M if sym != "general" else int(rng.integers(1, 80))
+        nnz = int(rng.integers(0, 300))
+        p = tmp_path / f"m{trial}.mtx"
+        fmt = fmts[trial % len(fmts)]
+        with open(p, "w") as f:
+            f.write(f"%%MatrixMarket matrix coordinate {field} {sym}\n%c1\n%c2\n{M} {N} {nnz}\n")
+            for _ in range(nnz):
+                i, j = int(rng.integers(1, M + 1)), int(rng.integers(1, N + 1))
+                if sym != "general" and j > i:
+                    i, j = j, i
+                sep = "\t" if trial % 2 else " "
+                f.write(f"{i}{sep}{j}" + ("" if field == "pattern" else sep + fmt % rng.normal(0, 1e3)) + "\n")
+        want = O.ref_load_mtx(str(p))
+        A = sp.io_load_csr(str(p))
+        assert (A.M, A.N) == (want[0], want[1])
+        assert np.array_equal(A.IRP, want[2])
+        assert np.array_equal(A.JA, want[3])
+        assert np.array_equal(bits(A.AS), bits(want[4]))
+        assert A.name == want[5]
