@@ -42,6 +42,7 @@ struct Knobs {
       int hll_vec = 4;         // vector width of the HLL headline kernel
       int hll_stream_cfg = -1;
       int regular_lpr = -1; // force lanes-per-row (log2) of the adaptive base launch
+      int force_wide = 0;   // use 64-bit row offsets even when NZ < 2^31 (tests)
       int warmup = 1, reps = 3;
 } g_knobs;
 
@@ -530,7 +531,7 @@ static spmv_b200_csr *csr_alloc_shell(long long M, long long n_local, long long 
       }
       auto *h = new spmv_b200_csr();
       h->M = M, h->N = n_local, h->NZ = NZ, h->col_offset = col_offset;
-      h->wide = NZ >= (1ll << 31) - 64;
+      h->wide = g_knobs.force_wide || NZ >= (1ll << 31) - 64;
       cudaGetDevice(&h->device);
       const size_t irp_bytes = (size_t)(M + 1) * (h->wide ? 8 : 4);
       // +16 entries of slack: bulk copies round the entry range out to x4
@@ -1260,6 +1261,8 @@ extern "C" int spmv_b200_set_knob(const char *key, int value) {
             g_knobs.hll_stream_cfg = value;
       else if (!strcmp(key, "regular_lpr"))
             g_knobs.regular_lpr = value;
+      else if (!strcmp(key, "force_wide"))
+            g_knobs.force_wide = value;
       else
             return fail(-EINVAL, "unknown knob %s", key);
       return 0;

@@ -1,1 +1,274 @@
-int main(void){return 0;}
+/* kbench.c -- kernel sweep tool: every CSR/HLL kernel variant on one matrix.
+ *
+ *   kbench <matrix> [--reps N] [--warmup N] [--flush] [--peak GBs] [--quick]
+ *                   [--only csr|hll]
+ *   <matrix>: c1 | c2 | c3 | c4 | poisson:NX:NY | stencil:NX:NY:NZ |
+ *             uniform:N:K | rmat:SCALE:EF | ragged:N:W | mtx:<path>
+ *
+ * Prints one line per (kernel, warps/block, knob) with min / median kernel
+ * time (CUDA events, matrix resident in HBM), GFLOP/s = 2 nnz / t, achieved
+ * GB/s on the minimum-traffic byte count B_min = 12 nnz + 4 (M+1) + 8 M + 8 N,
+ * its fraction of --peak, and the largest |dy| / sum|a x| against the host
+ * serial CSR loop of libspmv_host (a sanity check; the parity gate proper is
+ * tests/ with the oracle).  Plain C over the public C ABI: this is also the
+ * usage example of include/spmv_b200.h.
+ */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "csr.h"
+#include "hll.h"
+#include "spmv_b200.h"
+#include "spmv_gen.h"
+
+static int g_reps = 20, g_warmup = 3, g_flush = 0, g_quick = 0;
+static double g_peak = 6559.7; /* MEASURED_PEAKS.json hbm_gbs of this pool */
+static const char *g_only = "";
+
+static int cmp_d(const void *a, const void *b) {
+      double x = *(const double *)a, y = *(const double *)b;
+      return (x > y) - (x < y);
+}
+
+static sparse_csr *make_matrix(const char *spec) {
+      int a, b, c;
+      if (!strcmp(spec, "c1"))
+            return gen_poisson2d(1000, 1000);
+      if (!strcmp(spec, "c2"))
+            return gen_stencil27(128, 128, 128);
+      if (!strcmp(spec, "c3"))
+            return gen_uniform_random(16000000, 32, 42);
+      if (!strcmp(spec, "c4"))
+            return gen_rmat(24, 16, 0.57, 0.19, 0.19, 42);
+      if (sscanf(spec, "poisson:%d:%d", &a, &b) == 2)
+            return gen_poisson2d(a, b);
+      if (sscanf(spec, "stencil:%d:%d:%d", &a, &b, &c) == 3)
+            return gen_stencil27(a, b, c);
+      if (sscanf(spec, "uniform:%d:%d", &a, &b) == 2)
+            return gen_uniform_random(a, b, 42);
+      if (sscanf(spec, "rmat:%d:%d", &a, &b) == 2)
+            return gen_rmat(a, b, 0.57, 0.19, 0.19, 42);
+      if (sscanf(spec, "ragged:%d:%d", &a, &b) == 2)
+            return gen_ragged(a, b, 7);
+      if (!strncmp(spec, "mtx:", 4)) {
+            sparse_csr *A = io_load_csr(spec + 4);
+            return (uintptr_t)A > (uintptr_t)-4096 ? NULL : A;
+      }
+      return NULL;
+}
+
+struct ctx {
+      const sparse_csr *A;
+      double *d_x, *d_y;
+      double *y_host, *y_ref, *scale;
+      double bmin;
+};
+
+static double check(struct ctx *c) {
+      const int M = c->A->M;
+      spmv_b200_d2h(c->y_host, c->d_y, (size_t)M * 8, NULL);
+      spmv_b200_stream_sync(NULL);
+      double worst = 0.0;
+      for (int r = 0; r < M; ++r) {
+            const double err = fabs(c->y_host[r] - c->y_ref[r]);
+            const double rel = c->scale[r] > 0 ? err / c->scale[r] : (err > 0 ? INFINITY : 0);
+            if (rel > worst)
+                  worst = rel;
+      }
+      return worst;
+}
+
+static void report(struct ctx *c, const char *fmt, const char *kname, int wpb, const char *knob,
+                   double *ms, int launches) {
+      qsort(ms, (size_t)g_reps, sizeof *ms, cmp_d);
+      const double tmin = ms[0], tmed = ms[g_reps / 2];
+      const double gf = 2.0 * c->A->NZ / (tmed * 1e6);
+      const double gbs = c->bmin / (tmed * 1e6);
+      const double err = check(c);
+      printf("%-4s %-14s wpb=%-2d %-18s launches=%d  min %8.4f ms  med %8.4f ms  %8.1f GFLOP/s  "
+             "%7.1f GB/s  %5.1f%% of %.0f  maxrel %.2e %s\n",
+             fmt, kname, wpb, knob, launches, tmin, tmed, gf, gbs, 100.0 * gbs / g_peak, g_peak, err,
+             err <= 1e-12 ? "ok" : "PARITY-FAIL");
+      fflush(stdout);
+}
+
+static void poison_y(struct ctx *c) { spmv_b200_dmemset(c->d_y, 0xff, (size_t)c->A->M * 8, NULL); }
+
+static const char *k_csr_names[] = {"thread_row", "warp_row", "adaptive", "block_row", "stream_tma"};
+static const char *k_hll_names[] = {"thread_row_rm", "thread_row", "warp_hack_vec", "stream_tma"};
+
+int spmv_b200_set_knob(const char *key, int value);
+
+static void run_csr(struct ctx *c, spmv_b200_csr *h, int kernel, int wpb, const char *knob) {
+      double *ms = malloc(sizeof(double) * (size_t)g_reps);
+      poison_y(c);
+      if (spmv_b200_csr_time(h, kernel, wpb, c->d_x, c->d_y, g_warmup, g_reps, g_flush, ms, NULL)) {
+            printf("CSR  %-14s wpb=%-2d %-18s FAILED: %s\n", k_csr_names[kernel], wpb, knob,
+                   spmv_b200_last_error());
+      } else {
+            report(c, "CSR", k_csr_names[kernel], wpb, knob, ms, spmv_b200_csr_launches(h, kernel));
+      }
+      free(ms);
+}
+
+static void run_hll(struct ctx *c, spmv_b200_hll *h, int kernel, int wpb, const char *knob) {
+      double *ms = malloc(sizeof(double) * (size_t)g_reps);
+      poison_y(c);
+      if (spmv_b200_hll_time(h, kernel, wpb, c->d_x, c->d_y, g_warmup, g_reps, g_flush, ms, NULL)) {
+            printf("HLL  %-14s wpb=%-2d %-18s FAILED: %s\n", k_hll_names[kernel], wpb, knob,
+                   spmv_b200_last_error());
+      } else {
+            report(c, "HLL", k_hll_names[kernel], wpb, knob, ms, 1);
+      }
+      free(ms);
+}
+
+int main(int argc, char **argv) {
+      if (argc < 2) {
+            fprintf(stderr, "usage: kbench <matrix> [--reps N] [--warmup N] [--flush] [--peak GBs] "
+                            "[--quick] [--only csr|hll]\n");
+            return 2;
+      }
+      for (int i = 2; i < argc; ++i) {
+            if (!strcmp(argv[i], "--reps") && i + 1 < argc)
+                  g_reps = atoi(argv[++i]);
+            else if (!strcmp(argv[i], "--warmup") && i + 1 < argc)
+                  g_warmup = atoi(argv[++i]);
+            else if (!strcmp(argv[i], "--peak") && i + 1 < argc)
+                  g_peak = atof(argv[++i]);
+            else if (!strcmp(argv[i], "--only") && i + 1 < argc)
+                  g_only = argv[++i];
+            else if (!strcmp(argv[i], "--flush"))
+                  g_flush = 1;
+            else if (!strcmp(argv[i], "--quick"))
+                  g_quick = 1;
+      }
+      spmv_b200_devinfo info;
+      if (spmv_b200_device_info(&info)) {
+            fprintf(stderr, "kbench: %s\n", spmv_b200_last_error());
+            return 1;
+      }
+      printf("# device %s sm_%d%d, %d SMs, L2 %d MB, HBM %.1f GB\n", info.name, info.cc_major,
+             info.cc_minor, info.sm_count, info.l2_bytes_mb, info.hbm_bytes / 1e9);
+
+      sparse_csr *A = make_matrix(argv[1]);
+      if (!A) {
+            fprintf(stderr, "kbench: cannot build matrix '%s'\n", argv[1]);
+            return 1;
+      }
+      struct ctx c = {.A = A};
+      c.bmin = 12.0 * A->NZ + 4.0 * (A->M + 1) + 8.0 * A->M + 8.0 * A->N;
+      printf("# matrix %s M=%d N=%d NZ=%d  B_min=%.0f bytes  reps=%d warmup=%d flush_l2=%d\n", A->name,
+             A->M, A->N, A->NZ, c.bmin, g_reps, g_warmup, g_flush);
+
+      /* x in [0,1) from a fixed LCG; reference y and per-row tolerance scale */
+      double *x = malloc(sizeof(double) * (size_t)A->N);
+      c.y_host = malloc(sizeof(double) * (size_t)A->M);
+      c.y_ref = malloc(sizeof(double) * (size_t)A->M);
+      c.scale = malloc(sizeof(double) * (size_t)A->M);
+      unsigned long long s = 88172645463325252ull;
+      for (int i = 0; i < A->N; ++i) {
+            s ^= s << 13, s ^= s >> 7, s ^= s << 17;
+            x[i] = (double)(s >> 11) / 9007199254740992.0;
+      }
+#pragma omp parallel for schedule(static, 1024)
+      for (int r = 0; r < A->M; ++r) {
+            double acc = 0, sc = 0;
+            for (int k = A->IRP[r]; k < A->IRP[r + 1]; ++k) {
+                  const double p = A->AS[k] * x[A->JA[k]];
+                  acc += p, sc += fabs(p);
+            }
+            c.y_ref[r] = acc, c.scale[r] = sc;
+      }
+      c.d_x = spmv_b200_dmalloc((size_t)A->N * 8 + 256);
+      c.d_y = spmv_b200_dmalloc((size_t)A->M * 8 + 256);
+      if (!c.d_x || !c.d_y)
+            return 1;
+      spmv_b200_h2d(c.d_x, x, (size_t)A->N * 8, NULL);
+      spmv_b200_stream_sync(NULL);
+
+      static const int wpbs[] = {2, 4, 8, 16};
+      char knob[64];
+
+      if (strcmp(g_only, "hll")) {
+            spmv_b200_csr *h = spmv_b200_csr_create(A);
+            if (!h) {
+                  fprintf(stderr, "kbench: %s\n", spmv_b200_last_error());
+                  return 1;
+            }
+            int64_t plan[10];
+            spmv_b200_csr_plan_info(h, plan, 10);
+            printf("# csr bins rows: <=4:%lld <=8:%lld <=16:%lld <=32:%lld <=64:%lld warp:%lld "
+                   "block:%lld split:%lld regular=%lld base_kind=%lld\n",
+                   (long long)plan[0], (long long)plan[1], (long long)plan[2], (long long)plan[3],
+                   (long long)plan[4], (long long)plan[5], (long long)plan[6], (long long)plan[7],
+                   (long long)plan[8], (long long)plan[9]);
+            for (int w = 0; w < 3; ++w) {
+                  run_csr(&c, h, 0, wpbs[w], "-");
+                  run_csr(&c, h, 1, wpbs[w], "-");
+                  if (!g_quick && A->M <= 4000000)
+                        run_csr(&c, h, 3, wpbs[w], "-");
+            }
+            for (int w = 0; w < 4; ++w)
+                  run_csr(&c, h, 2, wpbs[w], "auto");
+            spmv_b200_set_knob("stream_hints", 0);
+            run_csr(&c, h, 2, 8, "auto,nohints");
+            spmv_b200_set_knob("stream_hints", 1);
+            for (int cfg = 0; cfg < 8; ++cfg) {
+                  spmv_b200_set_knob("csr_stream_cfg", cfg);
+                  snprintf(knob, sizeof knob, "cfg=%d", cfg);
+                  run_csr(&c, h, 4, 4, knob);
+            }
+            spmv_b200_set_knob("csr_stream_cfg", -1);
+            spmv_b200_csr_destroy(h);
+            if (!g_quick) {
+                  /* forced lanes-per-row of the regular base launch */
+                  for (int lg = 0; lg <= 5; ++lg) {
+                        spmv_b200_set_knob("regular_lpr", lg);
+                        h = spmv_b200_csr_create(A);
+                        snprintf(knob, sizeof knob, "lanes/row=%d", 1 << lg);
+                        run_csr(&c, h, 2, 8, knob);
+                        run_csr(&c, h, 2, 4, knob);
+                        spmv_b200_csr_destroy(h);
+                  }
+                  spmv_b200_set_knob("regular_lpr", -1);
+            }
+      }
+
+      if (strcmp(g_only, "csr")) {
+            /* HLL built on the device from the resident CSR */
+            spmv_b200_csr *h = spmv_b200_csr_create(A);
+            spmv_b200_hll *hh = h ? spmv_b200_hll_from_csr(h) : NULL;
+            if (!hh) {
+                  fprintf(stderr, "kbench: %s\n", spmv_b200_last_error());
+                  return 1;
+            }
+            spmv_b200_csr_destroy(h);
+            printf("# hll hacks=%lld slots=%lld (padding %.2f%%)\n",
+                   (long long)spmv_b200_hll_num_hacks(hh), (long long)spmv_b200_hll_slots(hh),
+                   100.0 * (spmv_b200_hll_slots(hh) - (double)A->NZ) / (A->NZ ? A->NZ : 1));
+            for (int w = 0; w < 4; ++w)
+                  run_hll(&c, hh, 1, wpbs[w], "-");
+            for (int v = 1; v <= 4; v *= 2) {
+                  spmv_b200_set_knob("hll_vec", v);
+                  snprintf(knob, sizeof knob, "vec=%d", v);
+                  for (int w = 0; w < 4; ++w)
+                        run_hll(&c, hh, 2, wpbs[w], knob);
+            }
+            spmv_b200_set_knob("hll_vec", 4);
+            for (int cfg = 0; cfg < 6; ++cfg) {
+                  spmv_b200_set_knob("hll_stream_cfg", cfg);
+                  snprintf(knob, sizeof knob, "cfg=%d", cfg);
+                  run_hll(&c, hh, 3, 4, knob);
+            }
+            spmv_b200_set_knob("hll_stream_cfg", -1);
+            spmv_b200_hll_destroy(hh);
+      }
+
+      spmv_b200_dfree(c.d_x);
+      spmv_b200_dfree(c.d_y);
+      csr_free(A);
+      return 0;
+}
