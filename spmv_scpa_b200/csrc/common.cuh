@@ -71,40 +71,55 @@ __device__ __forceinline__ uint64_t policy_evict_last() {
 
 // ------------------------------------------------------- streaming loads --
 // Matrix values / indices are read exactly once per SpMV: keep them out of
-// L1 (no_allocate) and first in line for L2 eviction.
+// L1 (no_allocate) and first in line for L2 eviction.  The asm statements are
+// deliberately NOT volatile: everything they read is constant for the whole
+// launch, and ptxas must be free to issue a batch of them back to back (a
+// volatile load pins program order and serialises load -> use -> load).
 __device__ __forceinline__ double ld_stream_f64(const double *p, uint64_t pol) {
       double v;
-      asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;"
+      asm("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;"
                    : "=d"(v)
                    : "l"(p), "l"(pol));
       return v;
 }
 __device__ __forceinline__ int ld_stream_s32(const int *p, uint64_t pol) {
       int v;
-      asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;"
+      asm("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;"
                    : "=r"(v)
                    : "l"(p), "l"(pol));
       return v;
 }
 __device__ __forceinline__ double2 ld_stream_f64x2(const double *p, uint64_t pol) {
       double2 v;
-      asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;"
+      asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;"
                    : "=d"(v.x), "=d"(v.y)
                    : "l"(p), "l"(pol));
       return v;
 }
 __device__ __forceinline__ int2 ld_stream_s32x2(const int *p, uint64_t pol) {
       int2 v;
-      asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.s32 {%0,%1}, [%2], %3;"
+      asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.s32 {%0,%1}, [%2], %3;"
                    : "=r"(v.x), "=r"(v.y)
                    : "l"(p), "l"(pol));
       return v;
 }
 __device__ __forceinline__ int4 ld_stream_s32x4(const int *p, uint64_t pol) {
       int4 v;
-      asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;"
+      asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;"
                    : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
                    : "l"(p), "l"(pol));
+      return v;
+}
+// Same L2 priority but allowed to live in L1: sub-warp row groups re-touch the
+// tail of a 32-byte sector on their next step.
+__device__ __forceinline__ double ld_stream_l1_f64(const double *p, uint64_t pol) {
+      double v;
+      asm("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+      return v;
+}
+__device__ __forceinline__ int ld_stream_l1_s32(const int *p, uint64_t pol) {
+      int v;
+      asm("ld.global.nc.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
       return v;
 }
 // 256-bit load (sm_100+): four doubles per lane, 1 KiB per warp instruction.
@@ -113,7 +128,7 @@ struct double4_t {
 };
 __device__ __forceinline__ double4_t ld_stream_f64x4(const double *p) {
       double4_t v;
-      asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.f64 {%0,%1,%2,%3}, [%4];"
+      asm("ld.global.nc.L1::no_allocate.L2::evict_first.v4.f64 {%0,%1,%2,%3}, [%4];"
                    : "=d"(v.a), "=d"(v.b), "=d"(v.c), "=d"(v.d)
                    : "l"(p));
       return v;
@@ -125,7 +140,7 @@ __device__ __forceinline__ double4_t ld_stream_f64x4(const double *p) {
 // push it out.
 __device__ __forceinline__ double ld_x(const double *p, uint64_t pol) {
       double v;
-      asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;"
+      asm("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;"
                    : "=d"(v)
                    : "l"(p), "l"(pol));
       return v;
@@ -146,6 +161,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
                    "r"(bytes)
                    : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
       asm volatile(

@@ -53,23 +53,78 @@ __global__ void __launch_bounds__(1024)
 
       const uint64_t pol_s = policy_evict_first();
       const uint64_t pol_x = policy_evict_last();
-      double acc = 0.0;
-#pragma unroll 4
-      for (OffT k = s + sub; k < e; k += LPR) {
-            double a;
-            int c;
-            if (HINTS) {
-                  a = ld_stream_f64(as + k, pol_s);
-                  c = ld_stream_s32(ja + k, pol_s);
-            } else {
-                  a = __ldg(as + k);
-                  c = __ldg(ja + k);
+      // Batches of U entries per lane: all index/value loads of a batch are
+      // issued before the first gather, all gathers before the first FMA, so
+      // U independent memory round trips overlap instead of chaining.
+      constexpr int U = 4;
+      double acc0 = 0.0, acc1 = 0.0;
+      for (OffT k = s + sub; k < e; k += LPR * U) {
+            double a[U], xv[U];
+            int c[U];
+            bool okm[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                  const OffT kk = k + u * LPR;
+                  const bool ok = kk < e;
+                  okm[u] = ok;
+                  if (HINTS && LPR >= 16) {
+                        a[u] = ok ? ld_stream_f64(as + kk, pol_s) : 0.0;
+                        c[u] = ok ? ld_stream_s32(ja + kk, pol_s) : 0;
+                  } else if (HINTS) {
+                        a[u] = ok ? ld_stream_l1_f64(as + kk, pol_s) : 0.0;
+                        c[u] = ok ? ld_stream_l1_s32(ja + kk, pol_s) : 0;
+                  } else {
+                        a[u] = ok ? __ldg(as + kk) : 0.0;
+                        c[u] = ok ? __ldg(ja + kk) : 0;
+                  }
             }
-            acc = fma(a, ld_x(x + c, pol_x), acc);
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                  xv[u] = okm[u] ? ld_x(x + c[u], pol_x) : 0.0;
+#pragma unroll
+            for (int u = 0; u < U; u += 2) {
+                  acc0 = fma(a[u], xv[u], acc0);
+                  acc1 = fma(a[u + 1], xv[u + 1], acc1);
+            }
       }
+      double acc = acc0 + acc1;
       acc = group_sum<LPR>(acc);
       if (sub == 0)
             store_y(y, row, acc, push);
+}
+
+// Strided partial dot product of one long row: entries first, first+step, ...
+// below `end`, in batches of 4 independent load -> gather -> FMA chains.
+template <typename OffT>
+__device__ __forceinline__ double long_row_partial(const double *__restrict__ as,
+                                                   const int *__restrict__ ja,
+                                                   const double *__restrict__ x, OffT first,
+                                                   OffT end, int step, uint64_t pol_s,
+                                                   uint64_t pol_x) {
+      constexpr int U = 4;
+      double acc0 = 0.0, acc1 = 0.0;
+      for (OffT k = first; k < end; k += (OffT)step * U) {
+            double a[U], xv[U];
+            int c[U];
+            bool okm[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                  const OffT kk = k + (OffT)u * step;
+                  const bool ok = kk < end;
+                  okm[u] = ok;
+                  a[u] = ok ? ld_stream_f64(as + kk, pol_s) : 0.0;
+                  c[u] = ok ? ld_stream_s32(ja + kk, pol_s) : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                  xv[u] = okm[u] ? ld_x(x + c[u], pol_x) : 0.0;
+#pragma unroll
+            for (int u = 0; u < U; u += 2) {
+                  acc0 = fma(a[u], xv[u], acc0);
+                  acc1 = fma(a[u + 1], xv[u + 1], acc1);
+            }
+      }
+      return acc0 + acc1;
 }
 
 // ------------------------------------------------------------------------
@@ -88,11 +143,7 @@ __global__ void __launch_bounds__(1024)
       const uint64_t pol_s = policy_evict_first();
       const uint64_t pol_x = policy_evict_last();
 
-      double acc = 0.0;
-#pragma unroll 4
-      for (OffT k = s + threadIdx.x; k < e; k += blockDim.x)
-            acc = fma(ld_stream_f64(as + k, pol_s), ld_x(x + ld_stream_s32(ja + k, pol_s), pol_x),
-                      acc);
+      double acc = long_row_partial<OffT>(as, ja, x, s + threadIdx.x, e, blockDim.x, pol_s, pol_x);
       acc = group_sum<32>(acc);
 
       const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -121,11 +172,8 @@ __global__ void __launch_bounds__(1024)
       const long long s = chunk_k0[blockIdx.x], e = chunk_k1[blockIdx.x];
       const uint64_t pol_s = policy_evict_first();
       const uint64_t pol_x = policy_evict_last();
-      double acc = 0.0;
-#pragma unroll 4
-      for (long long k = s + threadIdx.x; k < e; k += blockDim.x)
-            acc = fma(ld_stream_f64(as + k, pol_s), ld_x(x + ld_stream_s32(ja + k, pol_s), pol_x),
-                      acc);
+      double acc =
+          long_row_partial<long long>(as, ja, x, s + threadIdx.x, e, blockDim.x, pol_s, pol_x);
       acc = group_sum<32>(acc);
       const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
       if (lane == 0)
@@ -161,27 +209,99 @@ __global__ void csr_combine_kernel(const int *__restrict__ split_row,
 // row with more than CAP entries is skipped here (long-row launch).
 //
 // Kernel: persistent CTAs, CTA b owns tiles b, b+G, b+2G, ...  A ring of
-// STAGES shared-memory buffers; thread 0 arms stage s with expect_tx and
-// issues two cp.async.bulk copies (values, indices); everybody waits on the
-// stage's mbarrier, computes from shared memory, __syncthreads, and thread 0
-// refills the stage with the tile STAGES ahead.
+// STAGES shared-memory buffers, each filled by two cp.async.bulk copies
+// (values, indices) that complete on the stage's "full" mbarrier.
+//   WS = false  every thread computes; thread 0 also issues the copies; one
+//               __syncthreads per tile hands the stage back.
+//   WS = true   warp-specialised: one extra producer warp issues copies as
+//               soon as a stage's "empty" mbarrier (one arrival per consumer
+//               warp) completes; consumer warps never meet at a CTA barrier,
+//               so they drift apart and overlap each other's gather latency.
 //
 // Compute: LPR lanes per row (LPR = 1: thread per row).  Rows of a warp are
 // neighbours, so for banded matrices the 32 x-gathers of one step fall in a
-// few contiguous sectors.  For even row lengths the walk through the row is
-// rotated by the row's index so lanes start in different banks.
+// few contiguous sectors (ELL-like access on CSR).  For even row lengths the
+// walk through the row is rotated by the row's index so lanes start in
+// different shared-memory banks.
 // ------------------------------------------------------------------------
-template <int THREADS, int LPR, int STAGES, int CAP, int PASSES, typename OffT>
+template <int THREADS, int LPR, int STAGES, int CAP, int PASSES, bool WS>
 struct StreamCfg {
-      static constexpr int kThreads = THREADS;
+      static constexpr int kConsumers = THREADS;
+      static constexpr int kThreads = THREADS + (WS ? 32 : 0);
       static constexpr int kRowsPerPass = THREADS / LPR;
       static constexpr int kMaxRows = kRowsPerPass * PASSES;
       static constexpr int kCap = CAP; // entries per stage (multiple of 4)
-      static constexpr size_t kSmem = (size_t)STAGES * CAP * 12 + STAGES * 8 + 16;
+      static constexpr size_t kSmem = (size_t)STAGES * CAP * 12 + 2 * STAGES * 8 + 16;
 };
 
-template <int THREADS, int LPR, int STAGES, int CAP, int PASSES, typename OffT>
-__global__ void __launch_bounds__(THREADS)
+// All rows of one staged tile.  `gi` = row slot of this thread, `sub` = lane
+// within the row group.
+template <int LPR, int RPP, int PASSES, typename OffT>
+__device__ __forceinline__ void stream_tile_rows(const OffT *__restrict__ irp,
+                                                 const double *__restrict__ tas,
+                                                 const int *__restrict__ tja, int r0, int r1,
+                                                 long long kbase, int gi, int sub, long long ks,
+                                                 long long ke, const double *__restrict__ x,
+                                                 double *__restrict__ y, uint64_t pol_x,
+                                                 const PushArgs &push) {
+      int row = r0 + gi;
+#pragma unroll 1
+      for (int p = 0; p < PASSES; ++p) {
+            if (p > 0) {
+                  if (r0 + p * RPP >= r1)
+                        break; // uniform over the CTA
+                  row = r0 + p * RPP + gi;
+                  if (row < r1) {
+                        ks = (long long)irp[row] - kbase;
+                        ke = (long long)irp[row + 1] - kbase;
+                  }
+            }
+            const int len = row < r1 ? (int)(ke - ks) : 0;
+            const int base = (int)ks;
+            // Even row lengths put the rows of a warp in the same banks:
+            // start each row's walk at a different entry (two contiguous
+            // runs [start,len) + [0,start)).
+            int start = 0;
+            if (LPR == 1 && len > 1 && (len & 1) == 0)
+                  start = gi % len;
+            constexpr int U = 8;
+            double acc0 = 0.0, acc1 = 0.0;
+            auto walk = [&](int from, int to) {
+                  for (int j = from + sub; j < to; j += LPR * U) {
+                        double a[U], xv[U];
+                        int c[U];
+                        bool okm[U];
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                              const int jj = j + u * LPR;
+                              const bool ok = jj < to;
+                              okm[u] = ok;
+                              c[u] = ok ? tja[base + jj] : 0;
+                              a[u] = ok ? tas[base + jj] : 0.0;
+                        }
+#pragma unroll
+                        for (int u = 0; u < U; ++u)
+                              xv[u] = okm[u] ? ld_x(x + c[u], pol_x) : 0.0;
+#pragma unroll
+                        for (int u = 0; u < U; u += 2) {
+                              acc0 = fma(a[u], xv[u], acc0);
+                              acc1 = fma(a[u + 1], xv[u + 1], acc1);
+                        }
+                  }
+            };
+            walk(start, len);
+            if (start)
+                  walk(0, start);
+            double acc = acc0 + acc1;
+            if (LPR > 1)
+                  acc = group_sum<LPR>(acc);
+            if (sub == 0 && row < r1)
+                  store_y(y, row, acc, push);
+      }
+}
+
+template <int THREADS, int LPR, int STAGES, int CAP, int PASSES, bool WS, typename OffT>
+__global__ void __launch_bounds__(THREADS + (WS ? 32 : 0))
     csr_stream_kernel(const OffT *__restrict__ irp, const int *__restrict__ ja,
                       const double *__restrict__ as, const int *__restrict__ tile_row,
                       const long long *__restrict__ tile_k, int tile0, int n_tiles,
@@ -189,22 +309,24 @@ __global__ void __launch_bounds__(THREADS)
       extern __shared__ __align__(128) unsigned char smem_raw[];
       double *s_as = reinterpret_cast<double *>(smem_raw);
       int *s_ja = reinterpret_cast<int *>(smem_raw + (size_t)STAGES * CAP * 8);
-      uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)STAGES * CAP * 12);
+      uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)STAGES * CAP * 12);
+      uint64_t *empty = full + STAGES;
 
       constexpr int RPP = THREADS / LPR;
+      constexpr int CWARPS = THREADS / 32;
       const int tid = threadIdx.x;
-      const int gi = tid / LPR, sub = tid % LPR;
       const uint64_t pol_s = policy_evict_first();
       const uint64_t pol_x = policy_evict_last();
 
       if (tid == 0) {
-            for (int s = 0; s < STAGES; ++s)
-                  mbar_init(&bars[s], 1);
+            for (int s = 0; s < STAGES; ++s) {
+                  mbar_init(&full[s], 1);
+                  mbar_init(&empty[s], CWARPS);
+            }
             mbar_fence_init();
       }
       __syncthreads();
 
-      // number of tiles this CTA owns
       const int first = tile0 + blockIdx.x;
       const int last = tile0 + n_tiles;
       const int stride = gridDim.x;
@@ -214,24 +336,39 @@ __global__ void __launch_bounds__(THREADS)
             const long long k1 = (tile_k[t + 1] + 3) & ~3ll;
             const long long cnt = k1 - k0;
             if (cnt > 0 && cnt <= CAP) {
-                  mbar_expect_tx(&bars[stage], (uint32_t)(cnt * 12));
-                  bulk_g2s(s_as + (size_t)stage * CAP, as + k0, (uint32_t)(cnt * 8), &bars[stage],
+                  mbar_expect_tx(&full[stage], (uint32_t)(cnt * 12));
+                  bulk_g2s(s_as + (size_t)stage * CAP, as + k0, (uint32_t)(cnt * 8), &full[stage],
                            pol_s);
-                  bulk_g2s(s_ja + (size_t)stage * CAP, ja + k0, (uint32_t)(cnt * 4), &bars[stage],
+                  bulk_g2s(s_ja + (size_t)stage * CAP, ja + k0, (uint32_t)(cnt * 4), &full[stage],
                            pol_s);
             } else {
                   // nothing to copy (empty rows only, or a long row handled
                   // elsewhere): complete the phase with a zero-byte arrival
-                  mbar_expect_tx(&bars[stage], 0);
+                  mbar_expect_tx(&full[stage], 0);
             }
       };
 
-      if (tid == 0) {
+      if (WS && tid >= THREADS) {
+            // ---------------- producer warp: one lane drives the ring ----------
+            if (tid == THREADS) {
+                  int it = 0;
+                  for (int t = first; t < last; t += stride, ++it) {
+                        const int stage = it % STAGES;
+                        if (it >= STAGES)
+                              mbar_wait(&empty[stage], (uint32_t)(it / STAGES - 1) & 1u);
+                        issue(t, stage);
+                  }
+            }
+            return;
+      }
+
+      if (!WS && tid == 0) {
             int t = first;
             for (int s = 0; s < STAGES && t < last; ++s, t += stride)
                   issue(t, s);
       }
 
+      const int gi = tid / LPR, sub = tid % LPR;
       int it = 0;
       for (int t = first; t < last; t += stride, ++it) {
             const int stage = it % STAGES;
@@ -241,54 +378,29 @@ __global__ void __launch_bounds__(THREADS)
             const bool staged = ((tile_k[t + 1] + 3) & ~3ll) - kbase <= CAP;
 
             // row extent of pass 0 is fetched before waiting on the copy
-            int row = r0 + gi;
             long long ks = 0, ke = 0;
-            if (row < r1) {
-                  ks = (long long)irp[row] - kbase;
-                  ke = (long long)irp[row + 1] - kbase;
+            if (r0 + gi < r1) {
+                  ks = (long long)irp[r0 + gi] - kbase;
+                  ke = (long long)irp[r0 + gi + 1] - kbase;
             }
-            mbar_wait(&bars[stage], parity);
+            mbar_wait(&full[stage], parity);
 
-            if (staged) {
-                  const double *tas = s_as + (size_t)stage * CAP;
-                  const int *tja = s_ja + (size_t)stage * CAP;
-#pragma unroll 1
-                  for (int p = 0; p < PASSES; ++p) {
-                        if (p > 0) {
-                              if (r0 + p * RPP >= r1)
-                                    break; // uniform over the CTA
-                              row = r0 + p * RPP + gi;
-                              if (row < r1) {
-                                    ks = (long long)irp[row] - kbase;
-                                    ke = (long long)irp[row + 1] - kbase;
-                              }
-                        }
-                        const int len = row < r1 ? (int)(ke - ks) : 0;
-                        const int base = (int)ks;
-                        // rotate the walk for even lengths (bank spreading)
-                        int start = 0;
-                        if (LPR == 1 && len > 1 && (len & 1) == 0)
-                              start = gi % len;
-                        double acc = 0.0;
-#pragma unroll 4
-                        for (int j = sub; j < len; j += LPR) {
-                              int jj = j + start;
-                              jj = jj >= len ? jj - len : jj;
-                              const double a = tas[base + jj];
-                              const int c = tja[base + jj];
-                              acc = fma(a, ld_x(x + c, pol_x), acc);
-                        }
-                        if (LPR > 1)
-                              acc = group_sum<LPR>(acc);
-                        if (sub == 0 && row < r1)
-                              store_y(y, row, acc, push);
+            if (staged)
+                  stream_tile_rows<LPR, RPP, PASSES, OffT>(irp, s_as + (size_t)stage * CAP,
+                                                           s_ja + (size_t)stage * CAP, r0, r1,
+                                                           kbase, gi, sub, ks, ke, x, y, pol_x,
+                                                           push);
+            if (WS) {
+                  __syncwarp();
+                  if ((tid & 31) == 0)
+                        mbar_arrive(&empty[stage]);
+            } else {
+                  __syncthreads();
+                  if (tid == 0) {
+                        const int tn = t + STAGES * stride;
+                        if (tn < last)
+                              issue(tn, stage);
                   }
-            }
-            __syncthreads();
-            if (tid == 0) {
-                  const int tn = t + STAGES * stride;
-                  if (tn < last)
-                        issue(tn, stage);
             }
       }
 }

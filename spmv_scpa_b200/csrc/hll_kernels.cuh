@@ -46,21 +46,35 @@ __global__ void __launch_bounds__(1024)
       const long long row_base = h * kHack;
 
       if (VEC == 1) {
-            double acc = 0.0;
-#pragma unroll 4
-            for (int j = 0; j < width; ++j) {
-                  const int s = j * 32 + lane;
-                  double a;
-                  int c;
-                  if (HINTS) {
-                        a = ld_stream_f64(has + s, pol_s);
-                        c = ld_stream_s32(hja + s, pol_s);
-                  } else {
-                        a = __ldg(has + s);
-                        c = __ldg(hja + s);
+            constexpr int U = 4;
+            double acc0 = 0.0, acc1 = 0.0;
+            for (int j = 0; j < width; j += U) {
+                  double a[U], xv[U];
+                  int c[U];
+                  bool okm[U];
+#pragma unroll
+                  for (int u = 0; u < U; ++u) {
+                        const int s = (j + u) * 32 + lane;
+                        const bool ok = j + u < width;
+                        okm[u] = ok;
+                        if (HINTS) {
+                              a[u] = ok ? ld_stream_f64(has + s, pol_s) : 0.0;
+                              c[u] = ok ? ld_stream_s32(hja + s, pol_s) : 0;
+                        } else {
+                              a[u] = ok ? __ldg(has + s) : 0.0;
+                              c[u] = ok ? __ldg(hja + s) : 0;
+                        }
                   }
-                  acc = fma(a, ld_x(x + c, pol_x), acc);
+#pragma unroll
+                  for (int u = 0; u < U; ++u)
+                        xv[u] = okm[u] ? ld_x(x + c[u], pol_x) : 0.0;
+#pragma unroll
+                  for (int u = 0; u < U; u += 2) {
+                        acc0 = fma(a[u], xv[u], acc0);
+                        acc1 = fma(a[u + 1], xv[u + 1], acc1);
+                  }
             }
+            const double acc = acc0 + acc1;
             if (row_base + lane < M)
                   store_y(y, row_base + lane, acc, push);
       } else if (VEC == 2) {
@@ -191,13 +205,29 @@ __global__ void __launch_bounds__(WARPS * 32)
                   if (h < h1) {
                         const double *tas = s_as + (size_t)stage * CAP + (hb - s0);
                         const int *tja = s_ja + (size_t)stage * CAP + (hb - s0);
-                        double acc = 0.0;
-#pragma unroll 4
-                        for (int j = 0; j < width; ++j) {
-                              const double a = tas[j * 32 + lane];
-                              const int c = tja[j * 32 + lane];
-                              acc = fma(a, ld_x(x + c, pol_x), acc);
+                        constexpr int U = 8;
+                        double acc0 = 0.0, acc1 = 0.0;
+                        for (int j = 0; j < width; j += U) {
+                              double a[U], xv[U];
+                              int c[U];
+                              bool okm[U];
+#pragma unroll
+                              for (int u = 0; u < U; ++u) {
+                                    const bool ok = j + u < width;
+                                    okm[u] = ok;
+                                    c[u] = ok ? tja[(j + u) * 32 + lane] : 0;
+                                    a[u] = ok ? tas[(j + u) * 32 + lane] : 0.0;
+                              }
+#pragma unroll
+                              for (int u = 0; u < U; ++u)
+                                    xv[u] = okm[u] ? ld_x(x + c[u], pol_x) : 0.0;
+#pragma unroll
+                              for (int u = 0; u < U; u += 2) {
+                                    acc0 = fma(a[u], xv[u], acc0);
+                                    acc1 = fma(a[u + 1], xv[u + 1], acc1);
+                              }
                         }
+                        const double acc = acc0 + acc1;
                         const long long r = (long long)h * kHack + lane;
                         if (r < M)
                               store_y(y, r, acc, push);

@@ -396,23 +396,35 @@ void run_adaptive(const CsrArgs &a, const Segment &sg) {
       launch_split(a, sg.split);
 }
 
-// stream kernel configurations: {threads, lanes/row, stages, cap, passes}
+// stream kernel configurations: {consumer threads, lanes/row, stages, cap, passes, warp-specialised}
 #define STREAM_CONFIGS(X)                                                                          \
-      X(0, 128, 1, 2, 4096, 1)                                                                     \
-      X(1, 128, 1, 3, 2048, 1)                                                                     \
-      X(2, 256, 1, 2, 8192, 1)                                                                     \
-      X(3, 256, 2, 2, 4096, 1)                                                                     \
-      X(4, 128, 1, 2, 4096, 4)                                                                     \
-      X(5, 64, 1, 3, 2048, 1)                                                                      \
-      X(6, 256, 1, 3, 4096, 2)                                                                     \
-      X(7, 128, 1, 4, 2048, 2)
-constexpr int kNumStreamCfg = 8;
+      X(0, 128, 1, 2, 4096, 1, false)                                                              \
+      X(1, 256, 2, 2, 3584, 1, false)                                                              \
+      X(2, 256, 1, 2, 8192, 1, false)                                                              \
+      X(3, 256, 2, 2, 4096, 1, false)                                                              \
+      X(4, 128, 1, 2, 4096, 4, false)                                                              \
+      X(5, 64, 1, 3, 2048, 1, false)                                                               \
+      X(6, 512, 4, 2, 4096, 1, false)                                                              \
+      X(7, 512, 2, 2, 8192, 1, false)                                                              \
+      X(8, 256, 4, 2, 2048, 1, false)                                                              \
+      X(9, 256, 2, 3, 3584, 1, false)                                                              \
+      X(10, 256, 2, 2, 4096, 1, true)                                                              \
+      X(11, 256, 2, 3, 3584, 1, true)                                                              \
+      X(12, 512, 4, 2, 4096, 1, true)                                                              \
+      X(13, 512, 2, 2, 8192, 1, true)                                                              \
+      X(14, 128, 1, 3, 4096, 1, true)                                                              \
+      X(15, 256, 1, 2, 8192, 1, true)                                                              \
+      X(16, 256, 2, 4, 2048, 1, true)                                                              \
+      X(17, 128, 1, 2, 4096, 4, true)                                                              \
+      X(18, 256, 1, 2, 4096, 4, true)                                                              \
+      X(19, 256, 1, 2, 8192, 4, true)
+constexpr int kNumStreamCfg = 20;
 
 struct StreamShape {
       int threads, lpr, stages, cap, passes;
 };
 constexpr StreamShape kStreamShapes[kNumStreamCfg] = {
-#define X(id, t, l, s, c, p) {t, l, s, c, p},
+#define X(id, t, l, s, c, p, w) {t, l, s, c, p},
     STREAM_CONFIGS(X)
 #undef X
 };
@@ -423,21 +435,24 @@ int launch_stream_cfg(int cfg, const CsrArgs &a, const StreamPlan &sp) {
             return 0;
       const OffT *irp = static_cast<const OffT *>(a.h->d_irp);
       switch (cfg) {
-#define X(id, T, L, S, C, P)                                                                       \
+#define X(id, T, L, S, C, P, W)                                                                    \
       case id: {                                                                                   \
-            auto kern = csr_stream_kernel<T, L, S, C, P, OffT>;                                    \
-            constexpr size_t smem = StreamCfg<T, L, S, C, P, OffT>::kSmem;                         \
+            auto kern = csr_stream_kernel<T, L, S, C, P, W, OffT>;                                 \
+            using Cfg = StreamCfg<T, L, S, C, P, W>;                                               \
+            constexpr size_t smem = Cfg::kSmem;                                                    \
             static int occ = 0;                                                                    \
             if (!occ) {                                                                            \
                   B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                                  (int)smem));                                      \
-                  B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T, smem));   \
+                  B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern,              \
+                                                                          Cfg::kThreads, smem));   \
                   if (occ < 1)                                                                     \
                         return fail(-EINVAL, "stream cfg %d does not fit on an SM", id);           \
             }                                                                                      \
             const int grid = std::min(sp.n_tiles, occ * g_sm_count);                               \
-            kern<<<grid, T, smem, a.st>>>(irp, a.h->d_ja, a.h->d_as, sp.d_tile_row, sp.d_tile_k, 0, \
-                                          sp.n_tiles, a.x, a.y, a.push);                           \
+            kern<<<grid, Cfg::kThreads, smem, a.st>>>(irp, a.h->d_ja, a.h->d_as, sp.d_tile_row,    \
+                                                      sp.d_tile_k, 0, sp.n_tiles, a.x, a.y,        \
+                                                      a.push);                                     \
             break;                                                                                 \
       }
             STREAM_CONFIGS(X)
@@ -449,10 +464,17 @@ int launch_stream_cfg(int cfg, const CsrArgs &a, const StreamPlan &sp) {
       return 0;
 }
 
-int stream_cfg_for(int wpb) {
+// Configuration of the TMA-staged kernel for one segment.  Measured on B200
+// (profiles/kbench_*.txt): warp-specialised variants win everywhere; rows of
+// ~16+ entries want several lanes per row (more gathers in flight), short rows
+// want one thread per row and several passes per tile so a tile still carries
+// a few thousand entries.  warps_per_block picks the CTA size within a class.
+int stream_cfg_for(int wpb, double mean_len) {
       if (g_knobs.csr_stream_cfg >= 0 && g_knobs.csr_stream_cfg < kNumStreamCfg)
             return g_knobs.csr_stream_cfg;
-      return wpb <= 2 ? 5 : (wpb <= 4 ? 0 : 2);
+      if (mean_len >= 12.0)
+            return wpb <= 2 ? 10 : (wpb <= 4 ? 12 : 13);
+      return wpb <= 2 ? 17 : (wpb <= 4 ? 18 : 19);
 }
 
 template <typename OffT>
@@ -471,7 +493,8 @@ int run_kernel(spmv_b200_csr *h, int kernel, int wpb, Segment &sg, const CsrArgs
             launch_block_rows<OffT>(a, sg.r0, sg.r1 - sg.r0, nullptr);
             return 0;
       case SPMV_B200_CSR_STREAM: {
-            const int cfg = stream_cfg_for(wpb);
+            const double mean_len = sg.r1 > sg.r0 ? (double)(h->h_irp[sg.r1] - h->h_irp[sg.r0]) / (double)(sg.r1 - sg.r0) : 0.0;
+            const int cfg = stream_cfg_for(wpb, mean_len);
             StreamPlan &sp = sg.stream[cfg];
             if (!sp.built) {
                   const StreamShape &s = kStreamShapes[cfg];

@@ -1,0 +1,289 @@
+"""Row-partitioned, iterated SpMV over several GPUs: x_{k+1} = A x_k.
+
+NEW SURFACE -- the reference is single-GPU.  What it does offer
+is the partition rule: contiguous row ranges with balanced nnz, a range closed
+as soon as its running nnz reaches total/parts (partition_csr_rows, reference
+src/csr.c:218-276).  `balanced_row_cuts` restates that rule and additionally
+rounds cuts to hack boundaries (32 rows).
+
+One process per GPU (torch.distributed, NCCL over NVLink; gloo on CPU for the
+tests).  Rank r owns rows [r0, r1) of A and the matching slice of x.  Its rows
+reference the global column range [c0, c1) -- for a banded / stencil matrix
+that is the own slice plus a halo, for a general matrix it is everything
+(then the exchange degenerates to an all-gather).  The local x buffer covers
+[c0, c1); the shard's column indices are stored relative to c0.
+
+Per iteration:
+  1. boundary rows  = own rows some peer needs; computed FIRST
+  2. exchange       = those values travel to the peers' halo regions
+                      mode "nccl": batched isend/irecv on a side stream
+                      mode "push": the boundary-row kernel itself stores them
+                                   into the peers' buffers (CUDA IPC mapped, NVLink
+                                   peer stores from the SpMV epilogue) and a
+                                   1-element all-reduce orders the steps
+  3. interior rows  = everything else, on the compute stream, overlapping 2.
+x is double-buffered: step k reads X[k%2] and writes X[(k+1)%2].
+"""
+import numpy as np
+
+HACK = 32
+
+
+# ------------------------------------------------------------------ planning --
+def balanced_row_cuts(irp, parts, align=HACK):
+    """cuts[parts+1] over rows; greedy nnz balance as the reference's partition_csr_rows
+    (src/csr.c:218-276), each cut rounded UP to a multiple of `align`.  Trailing parts may
+    be empty when the matrix has fewer aligned blocks than parts."""
+    irp = np.asarray(irp, dtype=np.int64)
+    M = len(irp) - 1
+    total = int(irp[-1])
+    cuts = [0]
+    target = total / parts if parts else 0.0
+    running_from = 0
+    for _ in range(parts - 1):
+        # first row r such that nnz(rows[running_from..r]) >= target
+        want = irp[running_from] + target
+        r = int(np.searchsorted(irp, want, side="left"))  # irp[r] >= want  -> rows < r reach it
+        r = max(r, running_from + 1) if running_from < M else M
+        r = min(M, -(-r // align) * align)
+        cuts.append(r)
+        running_from = r
+    cuts.append(M)
+    return np.maximum.accumulate(np.asarray(cuts, dtype=np.int64))
+
+
+def column_range(ja, r0, r1):
+    """[c0, c1) touched by a shard; an empty shard needs only its own slice."""
+    if len(ja) == 0:
+        return r0, r1
+    return int(min(int(np.min(ja)), r0)), int(max(int(np.max(ja)) + 1, r1))
+
+
+class ExchangePlan:
+    """Who sends which global index ranges to whom.  Built from every rank's
+    (r0, r1, c0, c1); identical on all ranks."""
+
+    def __init__(self, rank, table):
+        self.rank = rank
+        self.table = [tuple(int(v) for v in row) for row in table]
+        r0, r1, c0, c1 = self.table[rank]
+        self.r0, self.r1, self.c0, self.c1 = r0, r1, c0, c1
+        self.recv = []  # (peer, g0, g1): x[g0:g1] arrives from peer
+        self.send = []  # (peer, g0, g1): own y[g0:g1] goes to peer
+        for p, (pr0, pr1, pc0, pc1) in enumerate(self.table):
+            if p == rank:
+                continue
+            g0, g1 = max(c0, pr0), min(c1, pr1)
+            if g0 < g1:
+                self.recv.append((p, g0, g1))
+            g0, g1 = max(pc0, r0), min(pc1, r1)
+            if g0 < g1:
+                self.send.append((p, g0, g1))
+        covered = sum(g1 - g0 for _, g0, g1 in self.recv) + (r1 - r0)
+        assert covered == c1 - c0, "row ranges must tile the needed column range"
+        # local row cut points: [0, lo) and [hi, M) are the rows peers need
+        lo = max([g1 for p, g0, g1 in self.send if g0 == r0] + [r0]) - r0
+        hi = min([g0 for p, g0, g1 in self.send if g1 == r1] + [r1]) - r0
+        M = r1 - r0
+        inner = [s for s in self.send if not (s[1] == r0 or s[2] == r1)]
+        if inner or lo >= hi:
+            # a peer needs rows from the middle (or everything): no interior to overlap
+            lo, hi = M, M
+        self.boundary_lo, self.boundary_hi = int(lo), int(hi)
+
+    @property
+    def cuts(self):
+        M = self.r1 - self.r0
+        return sorted({c for c in (self.boundary_lo, self.boundary_hi) if 0 < c < M})
+
+    @property
+    def segments(self):
+        """(row0, row1, is_boundary) local row segments in launch order: boundary first."""
+        M = self.r1 - self.r0
+        lo, hi = self.boundary_lo, self.boundary_hi
+        if lo >= M:  # everything is boundary
+            return [(0, M, True)] if M else []
+        segs = []
+        if lo > 0:
+            segs.append((0, lo, True))
+        if hi < M:
+            segs.append((hi, M, True))
+        segs.append((lo, hi, False))
+        return segs
+
+    def halo_bytes(self):
+        return 8 * sum(g1 - g0 for _, g0, g1 in self.recv)
+
+
+def gather_table(dist, r0, r1, c0, c1, device="cpu"):
+    """all-gather of the four integers that define every rank's shard."""
+    import torch
+    mine = torch.tensor([r0, r1, c0, c1], dtype=torch.int64, device=device)
+    out = [torch.zeros_like(mine) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, mine)
+    return [t.cpu().tolist() for t in out]
+
+
+# ----------------------------------------------------------------- execution --
+class DistSpMV:
+    """Iterated SpMV on one rank's shard.
+
+    shard:  object with .M, .N (= c1 - c0) and .spmv(x, y, kernel, warps_per_block, rows, push)
+            -- a CsrDevice on GPU; tests inject a CPU stand-in.
+    """
+
+    def __init__(self, dist, shard, plan, x0_own, device, mode="nccl", kernel=4, wpb=4):
+        import torch
+        self.torch, self.dist, self.shard, self.plan = torch, dist, shard, plan
+        self.mode, self.kernel, self.wpb = mode, kernel, wpb
+        self.device = device
+        n_local = plan.c1 - plan.c0
+        assert shard.N == n_local and shard.M == plan.r1 - plan.r0
+        self.own0 = plan.r0 - plan.c0
+        self.X = [torch.zeros(n_local, dtype=torch.float64, device=device) for _ in range(2)]
+        self.X[0][self.own0:self.own0 + shard.M] = x0_own
+        self.cuda = str(device).startswith("cuda")
+        self.step_no = 0
+        if self.cuda:
+            self.compute = torch.cuda.current_stream()
+            self.comm = torch.cuda.Stream()
+        self._peer_ptrs = None
+        self._flag = None
+        if mode == "push":
+            self._setup_push()
+        self._initial_exchange()
+
+    # -- helpers ---------------------------------------------------------------
+    def own(self, buf):
+        return self.X[buf][self.own0:self.own0 + self.shard.M]
+
+    def _p2p_ops(self, buf):
+        d, P = self.dist, self.plan
+        ops = []
+        for peer, g0, g1 in P.send:
+            ops.append(d.P2POp(d.isend, self.X[buf][g0 - P.c0:g1 - P.c0], peer))
+        for peer, g0, g1 in P.recv:
+            ops.append(d.P2POp(d.irecv, self.X[buf][g0 - P.c0:g1 - P.c0], peer))
+        return ops
+
+    def _exchange_nccl(self, buf):
+        ops = self._p2p_ops(buf)
+        if ops:
+            for req in self.dist.batch_isend_irecv(ops):
+                req.wait()
+
+    def _initial_exchange(self):
+        """Halo of x_0."""
+        self._exchange_nccl(0)
+        if self.cuda:
+            self.torch.cuda.synchronize()
+        self.dist.barrier()
+
+    def _setup_push(self):
+        """Map every peer's two x buffers into this process (CUDA IPC) so the boundary-row
+        kernel can store into them directly."""
+        import ctypes as C
+        from . import _lib as L
+        torch, d = self.torch, self.dist
+        world = d.get_world_size()
+        handles = torch.zeros(2 * 64, dtype=torch.uint8)
+        for b in range(2):
+            buf = (C.c_ubyte * 64)()
+            rc = L.b200.spmv_b200_ipc_export(C.c_void_p(self.X[b].data_ptr()), buf)
+            if rc:
+                raise RuntimeError("ipc export failed: " + L.last_error())
+            handles[64 * b:64 * b + 64] = torch.tensor(list(buf), dtype=torch.uint8)
+        # torch's caching allocator may hand out an interior pointer of a larger block;
+        # the IPC handle maps the BLOCK, so ship the offset inside it as well
+        base_off = torch.tensor([self._alloc_offset(self.X[0]), self._alloc_offset(self.X[1])],
+                                dtype=torch.int64)
+        h_all = [torch.zeros_like(handles) for _ in range(world)]
+        o_all = [torch.zeros_like(base_off) for _ in range(world)]
+        hd, od = handles.to(self.device), base_off.to(self.device)
+        h_all = [t.to(self.device) for t in h_all]
+        o_all = [t.to(self.device) for t in o_all]
+        d.all_gather(h_all, hd)
+        d.all_gather(o_all, od)
+        self._peer_ptrs = {}
+        peers = {p for p, _, _ in self.plan.send}
+        for p in peers:
+            ptrs = []
+            for b in range(2):
+                raw = bytes(h_all[p][64 * b:64 * b + 64].cpu().tolist())
+                hbuf = (C.c_ubyte * 64).from_buffer_copy(raw)
+                out = C.c_void_p()
+                rc = L.b200.spmv_b200_ipc_open(hbuf, C.byref(out))
+                if rc:
+                    raise RuntimeError("ipc open failed: " + L.last_error())
+                ptrs.append(out.value + int(o_all[p][b]))
+            self._peer_ptrs[p] = ptrs
+        self._flag = torch.zeros(1, dtype=torch.float32, device=self.device)
+
+    def _alloc_offset(self, t):
+        """Offset of tensor `t` inside its cudaMalloc block (the unit CUDA IPC exports)."""
+        import ctypes as C
+        cuda = C.CDLL("libcuda.so.1")
+        base, size = C.c_uint64(), C.c_size_t()
+        rc = cuda.cuMemGetAddressRange_v2(C.byref(base), C.byref(size), C.c_uint64(t.data_ptr()))
+        if rc != 0:
+            raise RuntimeError(f"cuMemGetAddressRange failed ({rc})")
+        return t.data_ptr() - base.value
+
+    # -- one iteration ---------------------------------------------------------
+    def step(self):
+        torch, P = self.torch, self.plan
+        src, dst = self.step_no % 2, (self.step_no + 1) % 2
+        x, y = self.X[src], self.own(dst)
+        segs = P.segments
+        if not self.cuda:  # CPU path of the tests: no streams
+            for r0, r1, _ in segs:
+                self.shard.spmv(x, y, kernel=self.kernel, warps_per_block=self.wpb, rows=(r0, r1))
+            self._exchange_nccl(dst)
+            self.step_no += 1
+            return
+
+        boundary = [s for s in segs if s[2]]
+        interior = [s for s in segs if not s[2]]
+        if self.mode == "push":
+            for r0, r1, _ in boundary:
+                push = []
+                for peer, g0, g1 in P.send:
+                    l0, l1 = g0 - P.r0, g1 - P.r0
+                    a, b = max(l0, r0), min(l1, r1)
+                    if a < b:
+                        pc0 = P.table[peer][2]
+                        # element (row a) of my slice lands at global index P.r0 + a in the peer's buffer
+                        dst_ptr = self._peer_ptrs[peer][dst] + 8 * (P.r0 + a - pc0)
+                        push.append((a, b, dst_ptr))
+                self.shard.spmv(x, y, kernel=self.kernel, warps_per_block=self.wpb, rows=(r0, r1),
+                                push=push[:2])
+                assert len(push) <= 2, "push epilogue supports two peers per boundary segment"
+            ev = torch.cuda.Event()
+            ev.record(self.compute)
+            with torch.cuda.stream(self.comm):
+                self.comm.wait_event(ev)
+                # orders the steps across ranks (pushes of step k land before anyone starts
+                # step k+1's boundary rows); carries no data
+                self.dist.all_reduce(self._flag)
+                done = torch.cuda.Event()
+                done.record(self.comm)
+        else:
+            for r0, r1, _ in boundary:
+                self.shard.spmv(x, y, kernel=self.kernel, warps_per_block=self.wpb, rows=(r0, r1))
+            ev = torch.cuda.Event()
+            ev.record(self.compute)
+            with torch.cuda.stream(self.comm):
+                self.comm.wait_event(ev)
+                ops = self._p2p_ops(dst)
+                reqs = self.dist.batch_isend_irecv(ops) if ops else []
+                for r in reqs:
+                    r.wait()
+                done = torch.cuda.Event()
+                done.record(self.comm)
+        for r0, r1, _ in interior:
+            self.shard.spmv(x, y, kernel=self.kernel, warps_per_block=self.wpb, rows=(r0, r1))
+        self.compute.wait_event(done)
+        self.step_no += 1
+
+    def result_own(self):
+        return self.own(self.step_no % 2)

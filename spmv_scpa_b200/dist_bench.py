@@ -1,0 +1,186 @@
+"""bench.py's multi-GPU leg (launched by torchrun, one rank per GPU).
+
+Workload: weak scaling of BASELINE configs[1] towards configs[4] -- rank r owns
+the 128^3 slab (planes [128 r, 128 r + 128)) of a 128 x 128 x 128*N 27-point
+stencil generated directly in HBM, and the job iterates x_{k+1} = A x_k with a
+one-plane halo exchange per neighbour per step (see dist.py).  `--workload c5`
+switches to the strong-scaling 512^3 case of configs[4] (planes split evenly).
+"""
+import json
+import os
+import statistics
+import time
+
+import numpy as np
+
+from . import api as sp
+from . import dist as D
+
+
+def x0_slice(g0, g1):
+    """x_0[g] in (0,1), a pure function of the global index (so every rank can
+    regenerate any part of it)."""
+    g = np.arange(g0, g1, dtype=np.uint64)
+    z = g + np.uint64(0x9E3779B97F4A7C15)
+    z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    z = z ^ (z >> np.uint64(31))
+    return ((z >> np.uint64(11)).astype(np.float64) + 0.5) / 9007199254740992.0
+
+
+def slab_geometry(args, rank, world):
+    if args.workload == "c5":
+        nx = ny = nz = 512
+    else:
+        nx = ny = 128
+        nz = 128 * world
+    per = nz // world
+    z0 = rank * per
+    z1 = nz if rank == world - 1 else z0 + per
+    return nx, ny, nz, z0, z1
+
+
+def run(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=device)
+
+    nx, ny, nz, z0, z1 = slab_geometry(args, rank, world)
+    plane = nx * ny
+    r0, r1 = z0 * plane, z1 * plane
+    c0, c1 = max(0, z0 - 1) * plane, min(nz, z1 + 1) * plane
+    table = D.gather_table(dist, r0, r1, c0, c1, device=device)
+    plan = D.ExchangePlan(rank, table)
+
+    t_build = time.time()
+    shard = sp.CsrDevice.stencil27(nx, ny, nz, z0, z1, col_offset=c0, n_local=c1 - c0, cuts=plan.cuts)
+    torch.cuda.synchronize()
+    t_build = time.time() - t_build
+    kernel = args.kernel if args.kernel is not None else 4
+    mode = os.environ.get("SPMV_B200_EXCHANGE", "push")
+
+    x0 = torch.from_numpy(x0_slice(r0, r1)).to(device)
+    it = D.DistSpMV(dist, shard, plan, x0, device, mode=mode, kernel=kernel, wpb=args.wpb)
+
+    # ---- parity of step 1 on this rank's rows against the oracle (bounded: own slab) ----
+    from oracle import oracle as O
+    it.step()
+    torch.cuda.synchronize()
+    y1 = it.result_own().cpu().numpy()
+    A_own = sp.gen_stencil27_rows(nx, ny, nz, r0, r1)
+    x_need = np.zeros(nx * ny * nz if (c1 - c0) * 4 > nx * ny * nz else 0)
+    # local view of x0 over [c0, c1), columns shifted like the shard's
+    xl = x0_slice(c0, c1)
+    ja_local = (A_own.JA.astype(np.int64) - c0).astype(np.int32)
+    y_ref = O.csr_spmv(A_own.M, A_own.IRP, ja_local, A_own.AS, xl)
+    bound = O.csr_abs_bound(A_own.M, A_own.IRP, ja_local, A_own.AS, xl)
+    ok, worst = O.check_tolerance(y1, y_ref, bound, 1e-12)
+    flag = torch.tensor([0 if ok else 1], device=device)
+    dist.all_reduce(flag)
+    if int(flag.item()) != 0:
+        raise SystemExit(f"rank {rank}: multi-GPU parity failed after step 1 (worst ratio {worst})")
+    del A_own, x_need
+
+    # ---- timed region ----
+    nnz_local = shard.NZ
+    nnz_t = torch.tensor([nnz_local], dtype=torch.int64, device=device)
+    dist.all_reduce(nnz_t)
+    nnz_total = int(nnz_t.item())
+    n_total = nx * ny * nz
+    bmin_total = sp.roofline_bytes(n_total, n_total, nnz_total)
+
+    def reset():
+        it.X[0].zero_()
+        it.X[1].zero_()
+        it.own(0).copy_(x0)
+        it.step_no = 0
+        it._initial_exchange()
+
+    reset()
+    for _ in range(args.warmup):
+        it.step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    c_before = sp.counters()["launches"]
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for k in range(args.steps):
+        it.step()
+    end.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms = torch.tensor([start.elapsed_time(end)], dtype=torch.float64, device=device)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    launches = sp.counters()["launches"] - c_before
+    finite = bool(torch.isfinite(it.result_own()).all().item())
+
+    # ---- kernel-only roofline on this rank: all rows, no exchange ----
+    xs = it.X[0]
+    ys = torch.zeros(shard.M, dtype=torch.float64, device=device)
+    per = shard.time(xs, ys, kernel=kernel, warps_per_block=args.wpb, warmup=3, reps=20)
+    bmin_local = sp.roofline_bytes(shard.M, shard.N, shard.NZ)
+    kern_ms = statistics.mean(per)
+
+    # ---- e2e: host x slice in, host y slice out, every step ----
+    xh = torch.from_numpy(x0_slice(r0, r1)).pin_memory()
+    yh = torch.empty(shard.M, dtype=torch.float64).pin_memory()
+
+    def e2e_step():
+        it.own(0).copy_(xh, non_blocking=True)
+        it._exchange_nccl(0)
+        shard.spmv(it.X[0], it.own(1), kernel=kernel, warps_per_block=args.wpb)
+        yh.copy_(it.own(1), non_blocking=True)
+        torch.cuda.synchronize()
+
+    for _ in range(2):
+        e2e_step()
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    dist.barrier()
+    e2e_dt = torch.tensor([(time.perf_counter() - t0) / args.steps], dtype=torch.float64, device=device)
+    dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
+
+    if rank == 0:
+        from bench import measured_peak, ClockSampler  # noqa: F401  (bench.py is on sys.path)
+        peak, peak_src = measured_peak()
+        ms_step = total_ms / args.steps
+        line = {
+            "metric": "fp64_spmv_gflops", "value": 2.0 * nnz_total / (ms_step * 1e6), "unit": "GFLOP/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "strong" if args.workload == "c5" else "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": (f"c5: 3D 27-point stencil 512^3, {world} z-slabs" if args.workload == "c5"
+                                    else f"c2-slabs: 3D 27-point stencil 128x128x{nz}, one 128^3 slab per GPU"),
+                       "format": "csr", "kernel": sp.CSR_KERNEL_NAMES[kernel], "warps_per_block": args.wpb,
+                       "rows": n_total, "nnz": nnz_total, "B_min_bytes": bmin_total,
+                       "iteration": "x_{k+1} = A x_k, halo exchange of one plane per neighbour per step",
+                       "exchange": mode, "halo_bytes_per_rank_per_step": plan.halo_bytes(),
+                       "l2_policy": "inputs larger than L2 (>= 0.7 GB streamed per GPU per step)",
+                       "shard_build_s": t_build, "finite": finite},
+            "hbm_gbs": bmin_total / (ms_step * 1e6),
+            "roofline": {"bound": "hbm", "achieved": bmin_local / (kern_ms * 1e6), "peak": peak, "unit": "GB/s",
+                         "frac": bmin_local / (kern_ms * 1e6) / peak, "traffic": None, "peak_source": peak_src,
+                         "kernel_ms_mean": kern_ms, "algorithmic_bytes": bmin_local,
+                         "note": "rank 0 shard, all rows in one call, no exchange"},
+            "cpu_baseline": None,
+            "e2e": {"value": 2.0 * nnz_total / (float(e2e_dt.item()) * 1e9), "unit": "GFLOP/s",
+                    "h2d_bytes_per_step": 8 * shard.M * world, "d2h_bytes_per_step": 8 * shard.M * world},
+            "gpu_launches": launches,
+            "clocks": None,
+            "parity": {"step1_vs_oracle": True, "worst_ratio_rank0": worst},
+        }
+        print(json.dumps(line))
+    dist.barrier()
+    dist.destroy_process_group()
+    return 0

@@ -216,7 +216,9 @@ int main(int argc, char **argv) {
             spmv_b200_set_knob("stream_hints", 0);
             run_csr(&c, h, 2, 8, "auto,nohints");
             spmv_b200_set_knob("stream_hints", 1);
-            for (int cfg = 0; cfg < 8; ++cfg) {
+            for (int w = 0; w < 3; ++w)
+                  run_csr(&c, h, 4, wpbs[w], "auto");
+            for (int cfg = g_quick ? 10 : 0; cfg < 20; ++cfg) {
                   spmv_b200_set_knob("csr_stream_cfg", cfg);
                   snprintf(knob, sizeof knob, "cfg=%d", cfg);
                   run_csr(&c, h, 4, 4, knob);
