@@ -52,13 +52,20 @@ def measured_peak():
         return FALLBACK_HBM_GBS, "fallback"
 
 
-def ncu_traffic(tag):
-    """Per-launch dram bytes of the dominant kernel from the committed ncu summary, or None."""
+def ncu_traffic(workload, kernel_symbol):
+    """Per-launch dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the
+    committed ncu summary (profiles/traffic.json, written by tools/summarize_profile.py), or None."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return json.load(f).get(tag)
+            allt = json.load(f)
+        keys = sorted(k for k in allt if k.endswith("_" + workload))
+        for k in reversed(keys):
+            for name, v in allt[k].items():
+                if name.startswith(kernel_symbol):
+                    return v
     except Exception:
-        return None
+        pass
+    return None
 
 
 WORKLOADS = {
@@ -214,6 +221,11 @@ def run_single(args):
 
     ck = args.kernel if args.kernel is not None else 4
     hk = args.kernel if args.kernel is not None else 2
+    KERNEL_SYMBOL = {("csr", 0): "csr_vec_kernel<1,", ("csr", 1): "csr_vec_kernel<32,",
+                     ("csr", 2): "csr_vec_kernel", ("csr", 3): "csr_block_row_kernel",
+                     ("csr", 4): "csr_stream_kernel", ("hll", 0): "hll_warp_kernel<1, 0",
+                     ("hll", 1): "hll_warp_kernel<1, 0", ("hll", 2): "hll_warp_kernel<1, 1",
+                     ("hll", 3): "hll_stream_kernel"}
     fmt = {"csr": (hcsr, ck, sp.CSR_KERNEL_NAMES[ck]),
            "hll": (hhll, hk, sp.HLL_KERNEL_NAMES[hk])}
 
@@ -274,7 +286,7 @@ def run_single(args):
             "launches": launches,
             "roofline": {"bound": "hbm", "achieved": bmin / (kern_ms * 1e6), "peak": peak,
                          "unit": "GB/s", "frac": bmin / (kern_ms * 1e6) / peak,
-                         "traffic": ncu_traffic(f"{args.workload}_{name}_{kname}"),
+                         "traffic": ncu_traffic(args.workload, KERNEL_SYMBOL[(name, k)]),
                          "peak_source": peak_src, "kernel_ms_mean": kern_ms,
                          "kernel_ms_min": min(per), "algorithmic_bytes": bmin},
         }

@@ -39,7 +39,7 @@ struct Counters {
 struct Knobs {
       int stream_hints = 1; // matrix streams: L1 no_allocate + L2 evict_first
       int csr_stream_cfg = -1; // -1: pick from warps_per_block
-      int hll_vec = 4;         // vector width of the HLL headline kernel
+      int hll_vec = 1;         // vector width of the HLL headline kernel (1 measured best on B200)
       int hll_stream_cfg = -1;
       int regular_lpr = -1; // force lanes-per-row (log2) of the adaptive base launch
       int force_wide = 0;   // use 64-bit row offsets even when NZ < 2^31 (tests)

@@ -23,7 +23,7 @@
 #include "spmv_b200.h"
 #include "spmv_gen.h"
 
-static int g_reps = 20, g_warmup = 3, g_flush = 0, g_quick = 0;
+static int g_reps = 20, g_warmup = 3, g_flush = 0, g_quick = 0, g_profile = 0;
 static double g_peak = 6559.7; /* MEASURED_PEAKS.json hbm_gbs of this pool */
 static const char *g_only = "";
 
@@ -144,6 +144,8 @@ int main(int argc, char **argv) {
                   g_flush = 1;
             else if (!strcmp(argv[i], "--quick"))
                   g_quick = 1;
+            else if (!strcmp(argv[i], "--profile"))
+                  g_profile = 1; /* only the headline kernels: for ncu captures */
       }
       spmv_b200_devinfo info;
       if (spmv_b200_device_info(&info)) {
@@ -191,6 +193,25 @@ int main(int argc, char **argv) {
 
       static const int wpbs[] = {2, 4, 8, 16};
       char knob[64];
+
+      if (g_profile) {
+            spmv_b200_csr *h = spmv_b200_csr_create(A);
+            spmv_b200_hll *hh = h ? spmv_b200_hll_from_csr(h) : NULL;
+            if (!h || !hh) {
+                  fprintf(stderr, "kbench: %s\n", spmv_b200_last_error());
+                  return 1;
+            }
+            run_csr(&c, h, 4, 4, "auto");
+            run_csr(&c, h, 2, 4, "auto");
+            spmv_b200_set_knob("hll_vec", 1);
+            run_hll(&c, hh, 2, 4, "vec=1");
+            spmv_b200_set_knob("hll_vec", 4);
+            run_hll(&c, hh, 2, 4, "vec=4");
+            run_hll(&c, hh, 3, 8, "auto");
+            spmv_b200_csr_destroy(h);
+            spmv_b200_hll_destroy(hh);
+            return 0;
+      }
 
       if (strcmp(g_only, "hll")) {
             spmv_b200_csr *h = spmv_b200_csr_create(A);
