@@ -381,8 +381,8 @@ def main():
         return run_reference_arm(args)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.gpus > 1 or world > 1:
-        from spmv_scpa_b200 import dist_bench
-        return dist_bench.run(args)
+        import bench_dist
+        return bench_dist.run(args)
     return run_single(args)
 
 

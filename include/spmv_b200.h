@@ -191,6 +191,18 @@ int spmv_b200_ipc_open(const unsigned char *handle64, void **d_ptr_out);
 int spmv_b200_ipc_close(void *d_ptr);
 int spmv_b200_enable_peer(int peer_device);
 
+/* Step ordering between ranks without a host round trip (multi-GPU halo push):
+ * spmv_b200_signal_peers  epoch := epoch + 1 (device word), then store it into
+ *                         each of the n peer slots (peer HBM mapped through IPC);
+ * spmv_b200_wait_peers    spin (at most max_spins polls per slot, then *d_error
+ *                         is set to 1 + slot index and the kernel returns) until
+ *                         each of my n slots holds a value >= my epoch.
+ * Both are single-thread kernels on `stream`, capturable in a CUDA graph. */
+int spmv_b200_signal_peers(void *d_epoch, int n, void *const *d_peer_slots,
+                           void *stream);
+int spmv_b200_wait_peers(const void *d_epoch, int n, void *const *d_my_slots,
+                         uint64_t max_spins, int *d_error, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -132,6 +132,8 @@ _sig(b200, "spmv_b200_ipc_export", C.c_int, vp, _p(C.c_ubyte))
 _sig(b200, "spmv_b200_ipc_open", C.c_int, _p(C.c_ubyte), _p(vp))
 _sig(b200, "spmv_b200_ipc_close", C.c_int, vp)
 _sig(b200, "spmv_b200_enable_peer", C.c_int, C.c_int)
+_sig(b200, "spmv_b200_signal_peers", C.c_int, vp, C.c_int, _p(vp), vp)
+_sig(b200, "spmv_b200_wait_peers", C.c_int, vp, C.c_int, _p(vp), C.c_uint64, vp, vp)
 
 # ---- host layer --------------------------------------------------------------
 _sig(host, "io_load_csr", vp, C.c_char_p)

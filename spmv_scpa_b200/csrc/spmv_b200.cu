@@ -1291,6 +1291,86 @@ extern "C" int spmv_b200_set_knob(const char *key, int value) {
       return 0;
 }
 
+// ------------------------------------------------- cross-GPU step ordering --
+// One process per GPU; every rank owns `flags[world]` and an `epoch` word in
+// its own HBM, mapped into the neighbours through CUDA IPC.  After the
+// boundary-row kernel of a step has pushed its halo rows into the neighbours,
+// signal_kernel bumps the local epoch and stores it into slot [my_rank] of
+// every neighbour's flags; before the next step's boundary rows, wait_kernel
+// spins (bounded) until every neighbour's slot has reached the local epoch.
+// No host round trip, no collective library call, capturable in a CUDA graph.
+namespace {
+
+struct PeerSlots {
+      int n;
+      unsigned long long *slot[8];
+};
+
+__global__ void signal_kernel(unsigned long long *epoch, PeerSlots peers) {
+      if (threadIdx.x != 0 || blockIdx.x != 0)
+            return;
+      const unsigned long long e = *epoch + 1;
+      *epoch = e;
+      __threadfence_system(); // halo rows pushed by earlier kernels are visible first
+      for (int i = 0; i < peers.n; ++i)
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peers.slot[i]), "l"(e)
+                         : "memory");
+}
+
+__global__ void wait_kernel(const unsigned long long *epoch, PeerSlots mine,
+                            unsigned long long max_spins, int *error) {
+      if (threadIdx.x != 0 || blockIdx.x != 0)
+            return;
+      if (*(volatile int *)error != 0)
+            return; // a previous wait already gave up: do not stall every later step
+      const unsigned long long want = *epoch;
+      for (int i = 0; i < mine.n; ++i) {
+            unsigned long long spins = 0, v;
+            for (;;) {
+                  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine.slot[i])
+                               : "memory");
+                  if (v >= want)
+                        break;
+                  if (++spins > max_spins) { // never hang the GPU: report and go on
+                        atomicExch(error, 1 + i);
+                        return;
+                  }
+                  __nanosleep(64);
+            }
+      }
+}
+
+} // namespace
+
+extern "C" int spmv_b200_signal_peers(void *d_epoch, int n, void *const *d_peer_slots,
+                                      void *stream) {
+      if (n < 0 || n > 8)
+            return fail(-EINVAL, "signal_peers: 0..8 peers");
+      PeerSlots p{};
+      p.n = n;
+      for (int i = 0; i < n; ++i)
+            p.slot[i] = static_cast<unsigned long long *>(d_peer_slots[i]);
+      signal_kernel<<<1, 32, 0, as_stream(stream)>>>(static_cast<unsigned long long *>(d_epoch), p);
+      ++g_counters.launches;
+      B200_CUDA(cudaGetLastError());
+      return 0;
+}
+
+extern "C" int spmv_b200_wait_peers(const void *d_epoch, int n, void *const *d_my_slots,
+                                    uint64_t max_spins, int *d_error, void *stream) {
+      if (n < 0 || n > 8)
+            return fail(-EINVAL, "wait_peers: 0..8 peers");
+      PeerSlots p{};
+      p.n = n;
+      for (int i = 0; i < n; ++i)
+            p.slot[i] = static_cast<unsigned long long *>(d_my_slots[i]);
+      wait_kernel<<<1, 32, 0, as_stream(stream)>>>(static_cast<const unsigned long long *>(d_epoch),
+                                                   p, max_spins, d_error);
+      ++g_counters.launches;
+      B200_CUDA(cudaGetLastError());
+      return 0;
+}
+
 // ------------------------------------------------------------------- IPC --
 extern "C" int spmv_b200_ipc_export(void *d_ptr, unsigned char *handle64) {
       static_assert(sizeof(cudaIpcMemHandle_t) == SPMV_B200_IPC_HANDLE_BYTES, "handle size");

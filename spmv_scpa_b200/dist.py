@@ -19,8 +19,12 @@ Per iteration:
                       mode "nccl": batched isend/irecv on a side stream
                       mode "push": the boundary-row kernel itself stores them
                                    into the peers' buffers (CUDA IPC mapped, NVLink
-                                   peer stores from the SpMV epilogue) and a
-                                   1-element all-reduce orders the steps
+                                   peer stores from the SpMV epilogue); a one-thread
+                                   signal kernel publishes the step number into the
+                                   neighbours' flag words and a one-thread wait kernel
+                                   holds back the next step's boundary rows until
+                                   every neighbour has signalled -- one stream, no
+                                   collective call, no host round trip
   3. interior rows  = everything else, on the compute stream, overlapping 2.
 x is double-buffered: step k reads X[k%2] and writes X[(k+1)%2].
 """
@@ -145,8 +149,10 @@ class DistSpMV:
         self.cuda = str(device).startswith("cuda")
         self.step_no = 0
         if self.cuda:
-            self.compute = torch.cuda.current_stream()
-            self.comm = torch.cuda.Stream()
+            # high priority: when the exchange kernel and the (SM-filling, persistent)
+            # interior kernel become runnable together, the exchange gets its SM first
+            self.comm = torch.cuda.Stream(priority=-1)
+        self.graph, self.graph_steps = None, 0
         self._peer_ptrs = None
         self._flag = None
         if mode == "push":
@@ -180,44 +186,52 @@ class DistSpMV:
         self.dist.barrier()
 
     def _setup_push(self):
-        """Map every peer's two x buffers into this process (CUDA IPC) so the boundary-row
-        kernel can store into them directly."""
+        """Map every neighbour's two x buffers and its flag words into this process (CUDA
+        IPC) so the boundary-row kernel can store into them directly and the signal kernel
+        can publish this rank's epoch."""
         import ctypes as C
         from . import _lib as L
         torch, d = self.torch, self.dist
-        world = d.get_world_size()
-        handles = torch.zeros(2 * 64, dtype=torch.uint8)
-        for b in range(2):
+        world, rank = d.get_world_size(), d.get_rank()
+        self._flags = torch.zeros(world, dtype=torch.int64, device=self.device)
+        self._epoch = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self._err = torch.zeros(1, dtype=torch.int32, device=self.device)
+        exported = [self.X[0], self.X[1], self._flags]
+        handles = torch.zeros(len(exported) * 64, dtype=torch.uint8)
+        for b, t in enumerate(exported):
             buf = (C.c_ubyte * 64)()
-            rc = L.b200.spmv_b200_ipc_export(C.c_void_p(self.X[b].data_ptr()), buf)
-            if rc:
+            if L.b200.spmv_b200_ipc_export(C.c_void_p(t.data_ptr()), buf):
                 raise RuntimeError("ipc export failed: " + L.last_error())
             handles[64 * b:64 * b + 64] = torch.tensor(list(buf), dtype=torch.uint8)
         # torch's caching allocator may hand out an interior pointer of a larger block;
         # the IPC handle maps the BLOCK, so ship the offset inside it as well
-        base_off = torch.tensor([self._alloc_offset(self.X[0]), self._alloc_offset(self.X[1])],
-                                dtype=torch.int64)
-        h_all = [torch.zeros_like(handles) for _ in range(world)]
-        o_all = [torch.zeros_like(base_off) for _ in range(world)]
-        hd, od = handles.to(self.device), base_off.to(self.device)
-        h_all = [t.to(self.device) for t in h_all]
-        o_all = [t.to(self.device) for t in o_all]
+        offs = torch.tensor([self._alloc_offset(t) for t in exported], dtype=torch.int64)
+        hd, od = handles.to(self.device), offs.to(self.device)
+        h_all = [torch.zeros_like(hd) for _ in range(world)]
+        o_all = [torch.zeros_like(od) for _ in range(world)]
         d.all_gather(h_all, hd)
         d.all_gather(o_all, od)
         self._peer_ptrs = {}
-        peers = {p for p, _, _ in self.plan.send}
-        for p in peers:
+        self._neighbours = sorted({p for p, _, _ in self.plan.send} | {p for p, _, _ in self.plan.recv})
+        opened = {}
+        for p in self._neighbours:
             ptrs = []
-            for b in range(2):
+            for b in range(len(exported)):
                 raw = bytes(h_all[p][64 * b:64 * b + 64].cpu().tolist())
-                hbuf = (C.c_ubyte * 64).from_buffer_copy(raw)
-                out = C.c_void_p()
-                rc = L.b200.spmv_b200_ipc_open(hbuf, C.byref(out))
-                if rc:
-                    raise RuntimeError("ipc open failed: " + L.last_error())
-                ptrs.append(out.value + int(o_all[p][b]))
+                if raw not in opened:  # several tensors may live in one allocator block
+                    hbuf = (C.c_ubyte * 64).from_buffer_copy(raw)
+                    out = C.c_void_p()
+                    if L.b200.spmv_b200_ipc_open(hbuf, C.byref(out)):
+                        raise RuntimeError("ipc open failed: " + L.last_error())
+                    opened[raw] = out.value
+                ptrs.append(opened[raw] + int(o_all[p][b]))
             self._peer_ptrs[p] = ptrs
-        self._flag = torch.zeros(1, dtype=torch.float32, device=self.device)
+        n = len(self._neighbours)
+        # slot [rank] of each neighbour's flags (I write), slot [p] of my flags (p writes)
+        self._peer_slots = (C.c_void_p * max(n, 1))(*[self._peer_ptrs[p][2] + 8 * rank for p in self._neighbours])
+        self._my_slots = (C.c_void_p * max(n, 1))(*[self._flags.data_ptr() + 8 * p for p in self._neighbours])
+        torch.cuda.synchronize()
+        d.barrier()
 
     def _alloc_offset(self, t):
         """Offset of tensor `t` inside its cudaMalloc block (the unit CUDA IPC exports)."""
@@ -244,7 +258,17 @@ class DistSpMV:
 
         boundary = [s for s in segs if s[2]]
         interior = [s for s in segs if not s[2]]
+        compute = torch.cuda.current_stream()  # the capture stream while a graph is being built
         if self.mode == "push":
+            import ctypes as C
+            from . import _lib as L
+            st = C.c_void_p(compute.cuda_stream)
+            n = len(self._neighbours)
+            # every neighbour has finished the boundary rows of the previous step: its
+            # pushes into X[src] have landed and it no longer reads the halo of X[dst]
+            if L.b200.spmv_b200_wait_peers(C.c_void_p(self._epoch.data_ptr()), n, self._my_slots,
+                                           1 << 21, C.c_void_p(self._err.data_ptr()), st):
+                raise RuntimeError(L.last_error())
             for r0, r1, _ in boundary:
                 push = []
                 for peer, g0, g1 in P.send:
@@ -252,26 +276,22 @@ class DistSpMV:
                     a, b = max(l0, r0), min(l1, r1)
                     if a < b:
                         pc0 = P.table[peer][2]
-                        # element (row a) of my slice lands at global index P.r0 + a in the peer's buffer
-                        dst_ptr = self._peer_ptrs[peer][dst] + 8 * (P.r0 + a - pc0)
-                        push.append((a, b, dst_ptr))
-                self.shard.spmv(x, y, kernel=self.kernel, warps_per_block=self.wpb, rows=(r0, r1),
-                                push=push[:2])
+                        # row a of my slice is global index P.r0 + a: its place in the peer's buffer
+                        push.append((a, b, self._peer_ptrs[peer][dst] + 8 * (P.r0 + a - pc0)))
                 assert len(push) <= 2, "push epilogue supports two peers per boundary segment"
-            ev = torch.cuda.Event()
-            ev.record(self.compute)
-            with torch.cuda.stream(self.comm):
-                self.comm.wait_event(ev)
-                # orders the steps across ranks (pushes of step k land before anyone starts
-                # step k+1's boundary rows); carries no data
-                self.dist.all_reduce(self._flag)
-                done = torch.cuda.Event()
-                done.record(self.comm)
+                self.shard.spmv(x, y, kernel=self.kernel, warps_per_block=self.wpb, rows=(r0, r1),
+                                push=push)
+            if L.b200.spmv_b200_signal_peers(C.c_void_p(self._epoch.data_ptr()), n, self._peer_slots, st):
+                raise RuntimeError(L.last_error())
+            for r0, r1, _ in interior:
+                self.shard.spmv(x, y, kernel=self.kernel, warps_per_block=self.wpb, rows=(r0, r1))
+            self.step_no += 1
+            return
         else:
             for r0, r1, _ in boundary:
                 self.shard.spmv(x, y, kernel=self.kernel, warps_per_block=self.wpb, rows=(r0, r1))
             ev = torch.cuda.Event()
-            ev.record(self.compute)
+            ev.record(compute)
             with torch.cuda.stream(self.comm):
                 self.comm.wait_event(ev)
                 ops = self._p2p_ops(dst)
@@ -282,8 +302,50 @@ class DistSpMV:
                 done.record(self.comm)
         for r0, r1, _ in interior:
             self.shard.spmv(x, y, kernel=self.kernel, warps_per_block=self.wpb, rows=(r0, r1))
-        self.compute.wait_event(done)
+        compute.wait_event(done)
         self.step_no += 1
+
+    # -- CUDA graph of two consecutive steps (one per x buffer) -----------------
+    def build_graph(self, steps=2):
+        """Capture `steps` (even) iterations -- kernels, the side-stream exchange and the
+        stream joins -- into one CUDA graph so a step costs one graph launch instead of a
+        dozen host-side calls.  Call after a few eager warm-up steps (plans built, NCCL
+        connections up) and on an even step number."""
+        torch = self.torch
+        assert self.cuda and steps % 2 == 0 and self.step_no % 2 == 0
+        torch.cuda.synchronize()
+        self.dist.barrier()
+        saved = self.step_no
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(steps):
+                self.step()
+        self.step_no = saved
+        self.graph, self.graph_steps = g, steps
+        torch.cuda.synchronize()
+        self.dist.barrier()
+
+    def run(self, k):
+        """k iterations, through the captured graph where possible."""
+        while k > 0:
+            if self.graph is not None and k >= self.graph_steps and self.step_no % 2 == 0:
+                self.graph.replay()
+                self.step_no += self.graph_steps
+                k -= self.graph_steps
+            else:
+                self.step()
+                k -= 1
+
+    def check_errors(self):
+        """Raise if a wait kernel gave up (a neighbour never signalled)."""
+        if self.mode == "push" and self.cuda:
+            e = int(self._err.item())
+            if e:
+                raise RuntimeError(f"rank {self.dist.get_rank()}: wait on neighbour slot {e - 1} timed out")
+
+    def close(self):
+        """Drop the captured graph before the process group goes away."""
+        self.graph = None
 
     def result_own(self):
         return self.own(self.step_no % 2)

@@ -11,7 +11,7 @@ from conftest import ROOT
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, mode, steps, q):
+def _worker(rank, world, port, mode, graph, steps, q):
     import sys
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
@@ -20,7 +20,7 @@ def _worker(rank, world, port, mode, steps, q):
     import torch.distributed as dist
     import spmv_scpa_b200 as sp
     from spmv_scpa_b200 import dist as D
-    from spmv_scpa_b200.dist_bench import x0_slice
+    from bench_dist import x0_slice
     from oracle import oracle as O
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
@@ -34,10 +34,19 @@ def _worker(rank, world, port, mode, steps, q):
     shard = sp.CsrDevice.stencil27(nx, ny, nz, z0, z1, col_offset=c0, n_local=c1 - c0, cuts=plan.cuts)
     x0 = torch.from_numpy(x0_slice(r0, r1)).to(dev)
     it = D.DistSpMV(dist, shard, plan, x0, dev, mode=mode, kernel=4, wpb=4)
-    for _ in range(steps):
-        it.step()
+    if graph:
+        it.step(); it.step()            # eager warm-up, then start again from x0 through the graph
+        it.build_graph(2)
+        it.X[0].zero_(); it.X[1].zero_(); it.own(0).copy_(x0); it.step_no = 0
+        it._initial_exchange()
+        it.run(steps)
+    else:
+        for _ in range(steps):
+            it.step()
     torch.cuda.synchronize()
+    it.check_errors()
     mine = it.result_own().cpu().numpy()
+    it.close()
     A = sp.gen_stencil27(nx, ny, nz)
     x = x0_slice(0, A.N)
     bound = None
@@ -50,8 +59,8 @@ def _worker(rank, world, port, mode, steps, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["nccl", "push"])
-def test_two_gpu_iterated_spmv(mode):
+@pytest.mark.parametrize("mode,graph", [("nccl", False), ("push", False), ("push", True), ("nccl", True)])
+def test_two_gpu_iterated_spmv(mode, graph):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -62,10 +71,10 @@ def test_two_gpu_iterated_spmv(mode):
     s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, mode, 4, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, mode, graph, 5 if graph else 4, q)) for r in range(2)]
     for p in procs:
         p.start()
-    out = [q.get(timeout=300) for _ in range(2)]
+    out = [q.get(timeout=100) for _ in range(2)]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
