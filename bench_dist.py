@@ -116,11 +116,16 @@ def run(args):
             graph_err = repr(e)[:200]
             it.graph = None
     reset()
-    it.run(args.warmup + (args.warmup % 2))
     torch.cuda.synchronize()
     dist.barrier()
     torch.cuda.synchronize()
     c_before = sp.counters()["launches"]
+    # The W warm-up steps run on the same stream immediately before the K timed steps, with
+    # no host synchronisation in between: the ranks leave the host barrier up to a few ms
+    # apart, and the first steps absorb that skew on the device (each rank's wait kernel
+    # paces it to its neighbours) instead of charging it to the timed region.
+    warm = args.warmup + (args.warmup % 2)
+    it.run(warm)
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
     it.run(args.steps)
@@ -133,9 +138,69 @@ def run(args):
     launches = sp.counters()["launches"] - c_before
     if it.graph is not None:
         # kernels replayed from the graph are not seen by the library's launch counter
-        launches = args.steps * len(plan.segments)
+        launches = args.steps * (len(plan.segments) + (2 if mode == "push" else 0))
     it.check_errors()
     finite = bool(torch.isfinite(it.result_own()).all().item())
+
+    diag = None
+    if os.environ.get("SPMV_B200_DIAG") == "1":
+        # where does a step's time go?  each piece alone, 20 back-to-back launches
+        def timed(fn, n=20):
+            torch.cuda.synchronize()
+            dist.barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(n):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / n * 1e3
+        segs = plan.segments
+        xb, yb = it.X[0], it.own(1)
+        diag = {}
+        for (s0, s1, isb) in segs:
+            diag[f"rows[{s0},{s1}){'B' if isb else 'I'}_us"] = timed(
+                lambda: shard.spmv(xb, yb, kernel=kernel, warps_per_block=args.wpb, rows=(s0, s1)))
+        diag["all_rows_us"] = timed(lambda: shard.spmv(xb, yb, kernel=kernel, warps_per_block=args.wpb))
+        diag["eager_step_us"] = timed(it.step)
+        if it.graph is not None:
+            diag["graph_2steps_us"] = timed(lambda: it.graph.replay())
+            # per-replay times on every rank (does one rank pace the other?)
+            torch.cuda.synchronize()
+            dist.barrier()
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(26)]
+            evs[0].record()
+            for i in range(25):
+                it.graph.replay()
+                evs[i + 1].record()
+            torch.cuda.synchronize()
+            mine = torch.tensor([evs[i].elapsed_time(evs[i + 1]) * 1e3 for i in range(25)],
+                                dtype=torch.float64, device=device)
+            allr = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(allr, mine)
+            diag["per_replay_us_by_rank"] = [[round(v, 1) for v in t.cpu().tolist()[:6]] for t in allr]
+
+            def variant(name, body, n=25):
+                torch.cuda.synchronize()
+                dist.barrier()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0 = time.perf_counter()
+                a.record()
+                for _ in range(n):
+                    body()
+                b.record()
+                cpu_us = (time.perf_counter() - t0) / n * 1e6
+                torch.cuda.synchronize()
+                diag[name] = {"gpu_us": a.elapsed_time(b) / n * 1e3, "cpu_issue_us": cpu_us}
+            variant("v1_back_to_back", lambda: it.graph.replay())
+            scratch = torch.cuda.Event()
+
+            def with_event():
+                it.graph.replay()
+                scratch.record()
+            variant("v2_event_after_each", with_event)
+            variant("v4_eager_step", it.step, n=50)
+        it.step_no = 0
 
     # ---- kernel-only roofline on this rank: all rows, no exchange ----
     xs = it.X[0]
@@ -182,7 +247,7 @@ def run(args):
                        "exchange": mode, "cuda_graph": it.graph is not None, "graph_error": graph_err,
                        "halo_bytes_per_rank_per_step": plan.halo_bytes(),
                        "l2_policy": "inputs larger than L2 (>= 0.7 GB streamed per GPU per step)",
-                       "shard_build_s": t_build, "finite": finite},
+                       "shard_build_s": t_build, "finite": finite, "diag": diag},
             "hbm_gbs": bmin_total / (ms_step * 1e6),
             "roofline": {"bound": "hbm", "achieved": bmin_local / (kern_ms * 1e6), "peak": peak, "unit": "GB/s",
                          "frac": bmin_local / (kern_ms * 1e6) / peak, "traffic": None, "peak_source": peak_src,
