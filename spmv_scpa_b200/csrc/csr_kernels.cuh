@@ -224,14 +224,20 @@ __global__ void csr_combine_kernel(const int *__restrict__ split_row,
 // walk through the row is rotated by the row's index so lanes start in
 // different shared-memory banks.
 // ------------------------------------------------------------------------
-template <int THREADS, int LPR, int STAGES, int CAP, int PASSES, bool WS>
+template <int THREADS, int LPR, int STAGES, int CAP, int PASSES, bool WS, bool SPLIT = false>
 struct StreamCfg {
       static constexpr int kConsumers = THREADS;
       static constexpr int kThreads = THREADS + (WS ? 32 : 0);
       static constexpr int kRowsPerPass = THREADS / LPR;
       static constexpr int kMaxRows = kRowsPerPass * PASSES;
       static constexpr int kCap = CAP; // entries per stage (multiple of 4)
-      static constexpr size_t kSmem = (size_t)STAGES * CAP * 12 + 2 * STAGES * 8 + 16;
+      static constexpr int kQueue = CAP / 32 + 8; // rows longer than 32 entries per tile
+      static constexpr int kIrpSlots = kMaxRows + 8; // staged row offsets per stage (SPLIT)
+      template <typename OffT>
+      static constexpr size_t smem() {
+            return (size_t)STAGES * CAP * 12 + 2 * STAGES * 8 + 16 +
+                   (SPLIT ? (size_t)(kQueue + 4) * 4 + 16 + (size_t)STAGES * kIrpSlots * sizeof(OffT) : 0);
+      }
 };
 
 // All rows of one staged tile.  `gi` = row slot of this thread, `sub` = lane
@@ -300,7 +306,96 @@ __device__ __forceinline__ void stream_tile_rows(const OffT *__restrict__ irp,
       }
 }
 
-template <int THREADS, int LPR, int STAGES, int CAP, int PASSES, bool WS, typename OffT>
+// Irregular tiles (power-law matrices): rows of wildly different lengths share
+// a tile, so the work is split by ENTRY, not by row.
+//   phase 1  every consumer thread strides over the staged entries and
+//            overwrites each value with value * x[col]   (balanced, gathers
+//            batched 4 deep);
+//   phase 2  thread per row adds up its (short) run of products; rows longer
+//            than 32 entries are queued in shared memory instead;
+//   phase 3  warps drain the queue, one warp per long row, shuffle reduction.
+// Named barrier 1 (consumer threads only) separates the phases.
+template <int THREADS, int PASSES, int CAP, typename OffT>
+__device__ __forceinline__ void stream_tile_products(const OffT *s_irp, double *tas, const int *tja,
+                                                     int r0, int r1, int r0a, long long kbase,
+                                                     int cnt, int tid,
+                                                     const double *__restrict__ x,
+                                                     double *__restrict__ y, uint64_t pol_x,
+                                                     const PushArgs &push, int *s_queue,
+                                                     int *s_queue_n) {
+      // batches of up to 8 entries per thread (deeper batches measured slower:
+      // profiles/r1_c4_*): loads, then gathers, then products back in place
+      constexpr int PER = (CAP + THREADS - 1) / THREADS;
+      constexpr int U = PER < 8 ? PER : 8;
+      if (tid == 0)
+            *s_queue_n = 0;
+      for (int j = tid; j < cnt; j += THREADS * U) {
+            double a[U], xv[U];
+            int c[U];
+            bool okm[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                  const int jj = j + u * THREADS;
+                  okm[u] = jj < cnt;
+                  c[u] = okm[u] ? tja[jj] : 0;
+                  a[u] = okm[u] ? tas[jj] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                  xv[u] = okm[u] ? ld_x(x + c[u], pol_x) : 0.0;
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                  if (okm[u])
+                        tas[j + u * THREADS] = a[u] * xv[u];
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
+
+#pragma unroll 1
+      for (int p = 0; p < PASSES; ++p) {
+            const int row = r0 + p * THREADS + tid;
+            if (r0 + p * THREADS >= r1)
+                  break;
+            if (row < r1) {
+                  const int s = (int)((long long)s_irp[row - r0a] - kbase);
+                  const int e = (int)((long long)s_irp[row - r0a + 1] - kbase);
+                  if (e - s <= 32) {
+                        // four independent shared-memory loads per step
+                        double acc0 = 0.0, acc1 = 0.0;
+                        for (int j = s; j < e; j += 4) {
+                              const double p0 = tas[j];
+                              const double p1 = j + 1 < e ? tas[j + 1] : 0.0;
+                              const double p2 = j + 2 < e ? tas[j + 2] : 0.0;
+                              const double p3 = j + 3 < e ? tas[j + 3] : 0.0;
+                              acc0 += p0 + p2;
+                              acc1 += p1 + p3;
+                        }
+                        store_y(y, row, acc0 + acc1, push);
+                  } else {
+                        s_queue[atomicAdd(s_queue_n, 1)] = row;
+                  }
+            }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
+
+      const int nq = *s_queue_n;
+      const int warp = tid >> 5, lane = tid & 31;
+      for (int q = warp; q < nq; q += THREADS / 32) {
+            const int row = s_queue[q];
+            const int s = (int)((long long)s_irp[row - r0a] - kbase);
+            const int e = (int)((long long)s_irp[row - r0a + 1] - kbase);
+            double acc = 0.0;
+            for (int j = s + lane; j < e; j += 32)
+                  acc += tas[j];
+            acc = group_sum<32>(acc);
+            if (lane == 0)
+                  store_y(y, row, acc, push);
+      }
+      // the stage was written through the generic proxy; order those writes
+      // before the bulk copy (async proxy) that refills it
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+template <int THREADS, int LPR, int STAGES, int CAP, int PASSES, bool WS, bool SPLIT, typename OffT>
 __global__ void __launch_bounds__(THREADS + (WS ? 32 : 0))
     csr_stream_kernel(const OffT *__restrict__ irp, const int *__restrict__ ja,
                       const double *__restrict__ as, const int *__restrict__ tile_row,
@@ -311,6 +406,14 @@ __global__ void __launch_bounds__(THREADS + (WS ? 32 : 0))
       int *s_ja = reinterpret_cast<int *>(smem_raw + (size_t)STAGES * CAP * 8);
       uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)STAGES * CAP * 12);
       uint64_t *empty = full + STAGES;
+      int *s_queue_n = reinterpret_cast<int *>(empty + STAGES + 1);
+      int *s_queue = s_queue_n + 4;
+      using Cfg = StreamCfg<THREADS, LPR, STAGES, CAP, PASSES, WS, SPLIT>;
+      // staged row offsets (entry-split mode only), 16-byte aligned
+      OffT *s_irp = reinterpret_cast<OffT *>(
+          (reinterpret_cast<uintptr_t>(s_queue + Cfg::kQueue) + 15) & ~uintptr_t(15));
+      constexpr int IRP_ALIGN = 16 / (int)sizeof(OffT); // rows per 16 bytes
+      static_assert(!SPLIT || WS, "the entry-split mode is only built warp-specialised");
 
       constexpr int RPP = THREADS / LPR;
       constexpr int CWARPS = THREADS / 32;
@@ -335,17 +438,29 @@ __global__ void __launch_bounds__(THREADS + (WS ? 32 : 0))
             const long long k0 = tile_k[t] & ~3ll;
             const long long k1 = (tile_k[t + 1] + 3) & ~3ll;
             const long long cnt = k1 - k0;
-            if (cnt > 0 && cnt <= CAP) {
-                  mbar_expect_tx(&full[stage], (uint32_t)(cnt * 12));
+            if (cnt > CAP) {
+                  // a long row handled elsewhere: complete the phase with a
+                  // zero-byte arrival
+                  mbar_expect_tx(&full[stage], 0);
+                  return;
+            }
+            uint32_t irp_bytes = 0;
+            int r0a = 0;
+            if (SPLIT) {
+                  r0a = tile_row[t] & ~(IRP_ALIGN - 1);
+                  const int n = (tile_row[t + 1] + 1 - r0a + IRP_ALIGN - 1) & ~(IRP_ALIGN - 1);
+                  irp_bytes = (uint32_t)n * (uint32_t)sizeof(OffT);
+            }
+            mbar_expect_tx(&full[stage], (uint32_t)(cnt * 12) + irp_bytes);
+            if (cnt > 0) {
                   bulk_g2s(s_as + (size_t)stage * CAP, as + k0, (uint32_t)(cnt * 8), &full[stage],
                            pol_s);
                   bulk_g2s(s_ja + (size_t)stage * CAP, ja + k0, (uint32_t)(cnt * 4), &full[stage],
                            pol_s);
-            } else {
-                  // nothing to copy (empty rows only, or a long row handled
-                  // elsewhere): complete the phase with a zero-byte arrival
-                  mbar_expect_tx(&full[stage], 0);
             }
+            if (SPLIT)
+                  bulk_g2s(s_irp + (size_t)stage * Cfg::kIrpSlots, irp + r0a, irp_bytes,
+                           &full[stage], pol_s);
       };
 
       if (WS && tid >= THREADS) {
@@ -379,17 +494,25 @@ __global__ void __launch_bounds__(THREADS + (WS ? 32 : 0))
 
             // row extent of pass 0 is fetched before waiting on the copy
             long long ks = 0, ke = 0;
-            if (r0 + gi < r1) {
+            if (!SPLIT && r0 + gi < r1) {
                   ks = (long long)irp[r0 + gi] - kbase;
                   ke = (long long)irp[r0 + gi + 1] - kbase;
             }
             mbar_wait(&full[stage], parity);
 
-            if (staged)
+            if (SPLIT) {
+                  const int cnt = (int)(((tile_k[t + 1] + 3) & ~3ll) - kbase);
+                  if (staged)
+                        stream_tile_products<THREADS, PASSES, CAP, OffT>(
+                            s_irp + (size_t)stage * Cfg::kIrpSlots, s_as + (size_t)stage * CAP,
+                            s_ja + (size_t)stage * CAP, r0, r1, r0 & ~(IRP_ALIGN - 1), kbase, cnt,
+                            tid, x, y, pol_x, push, s_queue, s_queue_n);
+            } else if (staged) {
                   stream_tile_rows<LPR, RPP, PASSES, OffT>(irp, s_as + (size_t)stage * CAP,
                                                            s_ja + (size_t)stage * CAP, r0, r1,
                                                            kbase, gi, sub, ks, ke, x, y, pol_x,
                                                            push);
+            }
             if (WS) {
                   __syncwarp();
                   if ((tid & 31) == 0)

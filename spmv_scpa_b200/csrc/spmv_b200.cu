@@ -396,35 +396,43 @@ void run_adaptive(const CsrArgs &a, const Segment &sg) {
       launch_split(a, sg.split);
 }
 
-// stream kernel configurations: {consumer threads, lanes/row, stages, cap, passes, warp-specialised}
+// stream kernel configurations:
+// {consumer threads, lanes/row, stages, cap, passes, warp-specialised, entry-split}
 #define STREAM_CONFIGS(X)                                                                          \
-      X(0, 128, 1, 2, 4096, 1, false)                                                              \
-      X(1, 256, 2, 2, 3584, 1, false)                                                              \
-      X(2, 256, 1, 2, 8192, 1, false)                                                              \
-      X(3, 256, 2, 2, 4096, 1, false)                                                              \
-      X(4, 128, 1, 2, 4096, 4, false)                                                              \
-      X(5, 64, 1, 3, 2048, 1, false)                                                               \
-      X(6, 512, 4, 2, 4096, 1, false)                                                              \
-      X(7, 512, 2, 2, 8192, 1, false)                                                              \
-      X(8, 256, 4, 2, 2048, 1, false)                                                              \
-      X(9, 256, 2, 3, 3584, 1, false)                                                              \
-      X(10, 256, 2, 2, 4096, 1, true)                                                              \
-      X(11, 256, 2, 3, 3584, 1, true)                                                              \
-      X(12, 512, 4, 2, 4096, 1, true)                                                              \
-      X(13, 512, 2, 2, 8192, 1, true)                                                              \
-      X(14, 128, 1, 3, 4096, 1, true)                                                              \
-      X(15, 256, 1, 2, 8192, 1, true)                                                              \
-      X(16, 256, 2, 4, 2048, 1, true)                                                              \
-      X(17, 128, 1, 2, 4096, 4, true)                                                              \
-      X(18, 256, 1, 2, 4096, 4, true)                                                              \
-      X(19, 256, 1, 2, 8192, 4, true)
-constexpr int kNumStreamCfg = 20;
+      X(0, 128, 1, 2, 4096, 1, false, false)                                                       \
+      X(1, 256, 2, 2, 3584, 1, false, false)                                                       \
+      X(2, 256, 1, 2, 8192, 1, false, false)                                                       \
+      X(3, 256, 2, 2, 4096, 1, false, false)                                                       \
+      X(4, 128, 1, 2, 4096, 4, false, false)                                                       \
+      X(5, 64, 1, 3, 2048, 1, false, false)                                                        \
+      X(6, 512, 4, 2, 4096, 1, false, false)                                                       \
+      X(7, 512, 2, 2, 8192, 1, false, false)                                                       \
+      X(8, 256, 4, 2, 2048, 1, false, false)                                                       \
+      X(9, 256, 2, 3, 3584, 1, false, false)                                                       \
+      X(10, 256, 2, 2, 4096, 1, true, false)                                                       \
+      X(11, 256, 2, 3, 3584, 1, true, false)                                                       \
+      X(12, 512, 4, 2, 4096, 1, true, false)                                                       \
+      X(13, 512, 2, 2, 8192, 1, true, false)                                                       \
+      X(14, 128, 1, 3, 4096, 1, true, false)                                                       \
+      X(15, 256, 1, 2, 8192, 1, true, false)                                                       \
+      X(16, 256, 2, 4, 2048, 1, true, false)                                                       \
+      X(17, 128, 1, 2, 4096, 4, true, false)                                                       \
+      X(18, 256, 1, 2, 4096, 4, true, false)                                                       \
+      X(19, 256, 1, 2, 8192, 4, true, false)                                                       \
+      X(20, 256, 1, 2, 4096, 4, true, true)                                                        \
+      X(21, 512, 1, 2, 4096, 2, true, true)                                                        \
+      X(22, 256, 1, 3, 2048, 4, true, true)                                                        \
+      X(23, 512, 1, 2, 8192, 2, true, true)                                                        \
+      X(24, 256, 1, 2, 4096, 8, true, true)                                                        \
+      X(25, 512, 1, 3, 4096, 2, true, true)                                                        \
+      X(26, 512, 1, 4, 2048, 2, true, true)
+constexpr int kNumStreamCfg = 27;
 
 struct StreamShape {
       int threads, lpr, stages, cap, passes;
 };
 constexpr StreamShape kStreamShapes[kNumStreamCfg] = {
-#define X(id, t, l, s, c, p, w) {t, l, s, c, p},
+#define X(id, t, l, s, c, p, w, sp) {t, l, s, c, p},
     STREAM_CONFIGS(X)
 #undef X
 };
@@ -435,11 +443,11 @@ int launch_stream_cfg(int cfg, const CsrArgs &a, const StreamPlan &sp) {
             return 0;
       const OffT *irp = static_cast<const OffT *>(a.h->d_irp);
       switch (cfg) {
-#define X(id, T, L, S, C, P, W)                                                                    \
+#define X(id, T, L, S, C, P, W, SP)                                                                \
       case id: {                                                                                   \
-            auto kern = csr_stream_kernel<T, L, S, C, P, W, OffT>;                                 \
-            using Cfg = StreamCfg<T, L, S, C, P, W>;                                               \
-            constexpr size_t smem = Cfg::kSmem;                                                    \
+            auto kern = csr_stream_kernel<T, L, S, C, P, W, SP, OffT>;                             \
+            using Cfg = StreamCfg<T, L, S, C, P, W, SP>;                                           \
+            constexpr size_t smem = Cfg::template smem<OffT>();                                    \
             static int occ = 0;                                                                    \
             if (!occ) {                                                                            \
                   B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, \
@@ -469,9 +477,11 @@ int launch_stream_cfg(int cfg, const CsrArgs &a, const StreamPlan &sp) {
 // ~16+ entries want several lanes per row (more gathers in flight), short rows
 // want one thread per row and several passes per tile so a tile still carries
 // a few thousand entries.  warps_per_block picks the CTA size within a class.
-int stream_cfg_for(int wpb, double mean_len) {
+int stream_cfg_for(int wpb, double mean_len, bool regular) {
       if (g_knobs.csr_stream_cfg >= 0 && g_knobs.csr_stream_cfg < kNumStreamCfg)
             return g_knobs.csr_stream_cfg;
+      if (!regular) // power-law / ragged: split tiles by entry, not by row
+            return wpb <= 4 ? 22 : 25;
       if (mean_len >= 12.0)
             return wpb <= 2 ? 10 : (wpb <= 4 ? 12 : 13);
       return wpb <= 2 ? 17 : (wpb <= 4 ? 18 : 19);
@@ -494,7 +504,7 @@ int run_kernel(spmv_b200_csr *h, int kernel, int wpb, Segment &sg, const CsrArgs
             return 0;
       case SPMV_B200_CSR_STREAM: {
             const double mean_len = sg.r1 > sg.r0 ? (double)(h->h_irp[sg.r1] - h->h_irp[sg.r0]) / (double)(sg.r1 - sg.r0) : 0.0;
-            const int cfg = stream_cfg_for(wpb, mean_len);
+            const int cfg = stream_cfg_for(wpb, mean_len, sg.regular);
             StreamPlan &sp = sg.stream[cfg];
             if (!sp.built) {
                   const StreamShape &s = kStreamShapes[cfg];
@@ -556,7 +566,8 @@ static spmv_b200_csr *csr_alloc_shell(long long M, long long n_local, long long 
       h->M = M, h->N = n_local, h->NZ = NZ, h->col_offset = col_offset;
       h->wide = g_knobs.force_wide || NZ >= (1ll << 31) - 64;
       cudaGetDevice(&h->device);
-      const size_t irp_bytes = (size_t)(M + 1) * (h->wide ? 8 : 4);
+      // +8 entries of slack: the entry-split kernel bulk-copies row offsets in 16-byte units
+      const size_t irp_bytes = (size_t)(M + 1 + 8) * (h->wide ? 8 : 4);
       // +16 entries of slack: bulk copies round the entry range out to x4
       if (cudaMalloc(&h->d_irp, irp_bytes) != cudaSuccess ||
           cudaMalloc(&h->d_ja, ((size_t)NZ + 16) * sizeof(int)) != cudaSuccess ||
@@ -566,6 +577,7 @@ static spmv_b200_csr *csr_alloc_shell(long long M, long long n_local, long long 
             spmv_b200_csr_destroy(h);
             return nullptr;
       }
+      cudaMemset(h->d_irp, 0, irp_bytes);
       cudaMemset(h->d_ja + NZ, 0, 16 * sizeof(int));
       cudaMemset(h->d_as + NZ, 0, 16 * sizeof(double));
       return h;

@@ -196,20 +196,26 @@ int main(int argc, char **argv) {
 
       if (g_profile) {
             spmv_b200_csr *h = spmv_b200_csr_create(A);
-            spmv_b200_hll *hh = h ? spmv_b200_hll_from_csr(h) : NULL;
-            if (!h || !hh) {
+            if (!h) {
                   fprintf(stderr, "kbench: %s\n", spmv_b200_last_error());
                   return 1;
             }
             run_csr(&c, h, 4, 4, "auto");
             run_csr(&c, h, 2, 4, "auto");
-            spmv_b200_set_knob("hll_vec", 1);
-            run_hll(&c, hh, 2, 4, "vec=1");
-            spmv_b200_set_knob("hll_vec", 4);
-            run_hll(&c, hh, 2, 4, "vec=4");
-            run_hll(&c, hh, 3, 8, "auto");
+            if (strcmp(g_only, "csr")) {
+                  spmv_b200_hll *hh = spmv_b200_hll_from_csr(h);
+                  if (!hh) {
+                        fprintf(stderr, "kbench: %s\n", spmv_b200_last_error());
+                        return 1;
+                  }
+                  run_hll(&c, hh, 2, 4, "vec=1");
+                  spmv_b200_set_knob("hll_vec", 4);
+                  run_hll(&c, hh, 2, 4, "vec=4");
+                  spmv_b200_set_knob("hll_vec", 1);
+                  run_hll(&c, hh, 3, 8, "auto");
+                  spmv_b200_hll_destroy(hh);
+            }
             spmv_b200_csr_destroy(h);
-            spmv_b200_hll_destroy(hh);
             return 0;
       }
 
@@ -239,7 +245,7 @@ int main(int argc, char **argv) {
             spmv_b200_set_knob("stream_hints", 1);
             for (int w = 0; w < 3; ++w)
                   run_csr(&c, h, 4, wpbs[w], "auto");
-            for (int cfg = g_quick ? 10 : 0; cfg < 20; ++cfg) {
+            for (int cfg = g_quick ? 10 : 0; cfg < 27; ++cfg) {
                   spmv_b200_set_knob("csr_stream_cfg", cfg);
                   snprintf(knob, sizeof knob, "cfg=%d", cfg);
                   run_csr(&c, h, 4, 4, knob);
