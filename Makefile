@@ -43,7 +43,7 @@ bin/kbench: tools/kbench.c $(LIBDIR)/libspmv_host.so
 	@mkdir -p bin
 	$(CC) $(CFLAGS) -o $@ $< -L$(LIBDIR) -lspmv_host -lspmv_b200 -Wl,-rpath,'$$ORIGIN/../$(LIBDIR)' -lm
 
-oracle:
+oracle: $(LIBDIR)/libspmv_b200.so
 	$(MAKE) -C oracle
 
 sass: $(LIBDIR)/libspmv_b200.so
