@@ -14,6 +14,8 @@ Contract (one JSON line on stdout, printed by rank 0):
            N>1: weak scaling -- rank r owns a 128^3 slab (planes
            [128 r, 128 r+128)) of a 128 x 128 x 128N stencil, x_{k+1} = A x_k
            with a halo exchange of one plane per neighbour each step.
+           --workload c5: BASELINE configs[4], the 512^3 stencil split into N
+           z-slabs (strong scaling; 46 GB and 64-bit row offsets at N=1).
   value    whole-job GFLOP/s with inputs resident in HBM.
   e2e      same metric through the reference-facing C ABI entry point
            (csr_spmv_cuda_halfwarp_row / hll_spmv_cuda_warp_block: HOST x in,
@@ -369,7 +371,8 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c5"],
+                    help="c5 = 3D 27-point stencil 512^3 (BASELINE configs[4]), z-slabs over --gpus ranks, strong scaling")
     ap.add_argument("--format", default="csr", choices=["csr", "hll"])
     ap.add_argument("--kernel", type=int, default=None)
     ap.add_argument("--wpb", type=int, default=4)
@@ -380,7 +383,10 @@ def main():
     if args.impl == "reference":
         return run_reference_arm(args)
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.gpus > 1 or world > 1:
+    if args.gpus > 1 or world > 1 or args.workload == "c5":
+        if "RANK" not in os.environ:  # plain `python bench.py --workload c5`: a 1-rank group
+            os.environ.update(RANK="0", WORLD_SIZE="1", LOCAL_RANK="0", MASTER_ADDR="127.0.0.1",
+                              MASTER_PORT=os.environ.get("MASTER_PORT", "29531"))
         import bench_dist
         return bench_dist.run(args)
     return run_single(args)

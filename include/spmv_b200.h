@@ -180,7 +180,7 @@ void spmv_b200_counters(int64_t *launches, int64_t *h2d_bytes,
                         int64_t *d2h_bytes);
 
 /* Experiment knobs used by bin/kbench sweeps ("stream_hints", "csr_stream_cfg",
- * "hll_vec", "hll_stream_cfg", "regular_lpr").  0 or -EINVAL.  Knobs that
+ * "hll_vec", "hll_stream_cfg", "regular_lpr", "adaptive_direct", "force_wide").  0 or -EINVAL.  Knobs that
  * change planning ("regular_lpr") must be set before a handle is created. */
 int spmv_b200_set_knob(const char *key, int value);
 

@@ -43,6 +43,8 @@ struct Knobs {
       int hll_stream_cfg = -1;
       int regular_lpr = -1; // force lanes-per-row (log2) of the adaptive base launch
       int force_wide = 0;   // use 64-bit row offsets even when NZ < 2^31 (tests)
+      int adaptive_direct = 0; // 1: the adaptive path never uses the TMA-staged kernel
+      int x_persist = 1;       // pin (part of) a large x in L2 with an access-policy window
       int warmup = 1, reps = 3;
 } g_knobs;
 
@@ -103,6 +105,50 @@ inline int blocks_for(long long threads, int block) {
 }
 
 inline int clamp_wpb(int wpb) { return wpb < 1 ? 1 : (wpb > 32 ? 32 : wpb); }
+
+// When x is too large to stay in L2 on its own (the streamed matrix keeps pushing it out),
+// reserve the persisting part of L2 for it: an access-policy window over x on the launching
+// stream, hit ratio = share of x that fits the carve-out.  Removed again after the launches.
+struct XWindow {
+      cudaStream_t st = nullptr;
+      bool active = false;
+      XWindow(const double *x, long long n, cudaStream_t stream) {
+            static int max_persist = -1, max_window = 0;
+            if (max_persist < 0) {
+                  int dev = 0;
+                  cudaGetDevice(&dev);
+                  cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+                  cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+                  if (max_persist > 0)
+                        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
+                  cudaGetLastError();
+            }
+            const long long bytes = n * 8;
+            if (!g_knobs.x_persist || max_persist <= 0 || bytes < (48ll << 20))
+                  return;
+            cudaStreamAttrValue v{};
+            v.accessPolicyWindow.base_ptr = const_cast<double *>(x);
+            v.accessPolicyWindow.num_bytes = (size_t)std::min<long long>(bytes, max_window);
+            v.accessPolicyWindow.hitRatio =
+                (float)std::min(1.0, 0.9 * (double)max_persist / (double)v.accessPolicyWindow.num_bytes);
+            v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            if (cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &v) ==
+                cudaSuccess) {
+                  st = stream;
+                  active = true;
+            }
+            cudaGetLastError();
+      }
+      ~XWindow() {
+            if (!active)
+                  return;
+            cudaStreamAttrValue v{};
+            v.accessPolicyWindow.num_bytes = 0;
+            cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v);
+            cudaGetLastError();
+      }
+};
 
 } // namespace
 
@@ -497,8 +543,15 @@ int run_kernel(spmv_b200_csr *h, int kernel, int wpb, Segment &sg, const CsrArgs
             launch_vec<OffT>(a, 5, sg.r0, sg.r1 - sg.r0, nullptr, -1);
             return 0;
       case SPMV_B200_CSR_ADAPTIVE:
-            run_adaptive<OffT>(a, sg);
-            return 0;
+            // Adaptive = per segment, the kernel family that measures best for its row-length
+            // profile: a regular segment (one length bin holds >= 90 % of the rows) streams
+            // through the TMA-staged tile kernel, which also bins its own long rows; an
+            // irregular one goes through the direct binned kernels.
+            if (!sg.regular || g_knobs.adaptive_direct) {
+                  run_adaptive<OffT>(a, sg);
+                  return 0;
+            }
+            return run_kernel<OffT>(h, SPMV_B200_CSR_STREAM, wpb, sg, a);
       case SPMV_B200_CSR_BLOCK_ROW:
             launch_block_rows<OffT>(a, sg.r0, sg.r1 - sg.r0, nullptr);
             return 0;
@@ -529,6 +582,7 @@ int csr_run(spmv_b200_csr *h, int kernel, int wpb, long long row0, long long row
             return fail(-EINVAL, "null CSR handle");
       wpb = clamp_wpb(wpb);
       CsrArgs a{h, d_x, d_y, push, as_stream(stream), 32 * wpb};
+      XWindow xwin(d_x, h->N, a.st);
       bool any = false;
       for (auto &sg : h->segs) {
             if (sg.r0 < row0 || sg.r1 > row1)
@@ -798,7 +852,15 @@ extern "C" int spmv_b200_csr_launches(const spmv_b200_csr *h, int kernel) {
       for (auto &sg : h->segs) {
             if (sg.r1 == sg.r0)
                   continue;
-            if (kernel == SPMV_B200_CSR_ADAPTIVE) {
+            if (kernel == SPMV_B200_CSR_ADAPTIVE && sg.regular && !g_knobs.adaptive_direct) {
+                  n += 1;
+                  for (auto &kv : sg.stream) {
+                        for (int k = 5; k < 7; ++k)
+                              n += kv.second.long_lists[k].n > 0;
+                        n += kv.second.split.n_rows ? 2 : 0;
+                        break;
+                  }
+            } else if (kernel == SPMV_B200_CSR_ADAPTIVE) {
                   n += sg.regular ? 1 : 0;
                   for (int k = 0; k < 7; ++k)
                         if (!(sg.regular && k <= sg.base_kind))
@@ -953,6 +1015,7 @@ int hll_run(spmv_b200_hll *h, int kernel, int wpb, const double *d_x, double *d_
             return 0;
       wpb = clamp_wpb(wpb);
       cudaStream_t st = as_stream(stream);
+      XWindow xwin(d_x, h->N, st);
       const int threads = 32 * wpb;
       const int grid = blocks_for(h->n_hacks * 32, threads);
       switch (kernel) {
@@ -1298,6 +1361,10 @@ extern "C" int spmv_b200_set_knob(const char *key, int value) {
             g_knobs.regular_lpr = value;
       else if (!strcmp(key, "force_wide"))
             g_knobs.force_wide = value;
+      else if (!strcmp(key, "adaptive_direct"))
+            g_knobs.adaptive_direct = value;
+      else if (!strcmp(key, "x_persist"))
+            g_knobs.x_persist = value;
       else
             return fail(-EINVAL, "unknown knob %s", key);
       return 0;

@@ -99,8 +99,6 @@ static void poison_y(struct ctx *c) { spmv_b200_dmemset(c->d_y, 0xff, (size_t)c-
 static const char *k_csr_names[] = {"thread_row", "warp_row", "adaptive", "block_row", "stream_tma"};
 static const char *k_hll_names[] = {"thread_row_rm", "thread_row", "warp_hack_vec", "stream_tma"};
 
-int spmv_b200_set_knob(const char *key, int value);
-
 static void run_csr(struct ctx *c, spmv_b200_csr *h, int kernel, int wpb, const char *knob) {
       double *ms = malloc(sizeof(double) * (size_t)g_reps);
       poison_y(c);
@@ -144,7 +142,12 @@ int main(int argc, char **argv) {
                   g_flush = 1;
             else if (!strcmp(argv[i], "--quick"))
                   g_quick = 1;
-            else if (!strcmp(argv[i], "--profile"))
+            else if (!strcmp(argv[i], "--knob") && i + 1 < argc) {
+                  char key[64];
+                  int val = 0;
+                  if (sscanf(argv[++i], "%63[^=]=%d", key, &val) == 2)
+                        spmv_b200_set_knob(key, val);
+            } else if (!strcmp(argv[i], "--profile"))
                   g_profile = 1; /* only the headline kernels: for ncu captures */
       }
       spmv_b200_devinfo info;
@@ -201,7 +204,9 @@ int main(int argc, char **argv) {
                   return 1;
             }
             run_csr(&c, h, 4, 4, "auto");
-            run_csr(&c, h, 2, 4, "auto");
+            spmv_b200_set_knob("adaptive_direct", 1);
+            run_csr(&c, h, 2, 4, "direct-binned");
+            spmv_b200_set_knob("adaptive_direct", 0);
             if (strcmp(g_only, "csr")) {
                   spmv_b200_hll *hh = spmv_b200_hll_from_csr(h);
                   if (!hh) {
@@ -240,9 +245,13 @@ int main(int argc, char **argv) {
             }
             for (int w = 0; w < 4; ++w)
                   run_csr(&c, h, 2, wpbs[w], "auto");
+            spmv_b200_set_knob("adaptive_direct", 1);
+            for (int w = 0; w < 3; ++w)
+                  run_csr(&c, h, 2, wpbs[w], "direct-binned");
             spmv_b200_set_knob("stream_hints", 0);
-            run_csr(&c, h, 2, 8, "auto,nohints");
+            run_csr(&c, h, 2, 8, "direct,nohints");
             spmv_b200_set_knob("stream_hints", 1);
+            spmv_b200_set_knob("adaptive_direct", 0);
             for (int w = 0; w < 3; ++w)
                   run_csr(&c, h, 4, wpbs[w], "auto");
             for (int cfg = g_quick ? 10 : 0; cfg < 27; ++cfg) {
@@ -254,6 +263,7 @@ int main(int argc, char **argv) {
             spmv_b200_csr_destroy(h);
             if (!g_quick) {
                   /* forced lanes-per-row of the regular base launch */
+                  spmv_b200_set_knob("adaptive_direct", 1);
                   for (int lg = 0; lg <= 5; ++lg) {
                         spmv_b200_set_knob("regular_lpr", lg);
                         h = spmv_b200_csr_create(A);
@@ -263,6 +273,7 @@ int main(int argc, char **argv) {
                         spmv_b200_csr_destroy(h);
                   }
                   spmv_b200_set_knob("regular_lpr", -1);
+                  spmv_b200_set_knob("adaptive_direct", 0);
             }
       }
 
