@@ -44,7 +44,6 @@ struct Knobs {
       int regular_lpr = -1; // force lanes-per-row (log2) of the adaptive base launch
       int force_wide = 0;   // use 64-bit row offsets even when NZ < 2^31 (tests)
       int adaptive_direct = 0; // 1: the adaptive path never uses the TMA-staged kernel
-      int x_persist = 1;       // pin (part of) a large x in L2 with an access-policy window
       int warmup = 1, reps = 3;
 } g_knobs;
 
@@ -106,49 +105,11 @@ inline int blocks_for(long long threads, int block) {
 
 inline int clamp_wpb(int wpb) { return wpb < 1 ? 1 : (wpb > 32 ? 32 : wpb); }
 
-// When x is too large to stay in L2 on its own (the streamed matrix keeps pushing it out),
-// reserve the persisting part of L2 for it: an access-policy window over x on the launching
-// stream, hit ratio = share of x that fits the carve-out.  Removed again after the launches.
-struct XWindow {
-      cudaStream_t st = nullptr;
-      bool active = false;
-      XWindow(const double *x, long long n, cudaStream_t stream) {
-            static int max_persist = -1, max_window = 0;
-            if (max_persist < 0) {
-                  int dev = 0;
-                  cudaGetDevice(&dev);
-                  cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
-                  cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
-                  if (max_persist > 0)
-                        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
-                  cudaGetLastError();
-            }
-            const long long bytes = n * 8;
-            if (!g_knobs.x_persist || max_persist <= 0 || bytes < (48ll << 20))
-                  return;
-            cudaStreamAttrValue v{};
-            v.accessPolicyWindow.base_ptr = const_cast<double *>(x);
-            v.accessPolicyWindow.num_bytes = (size_t)std::min<long long>(bytes, max_window);
-            v.accessPolicyWindow.hitRatio =
-                (float)std::min(1.0, 0.9 * (double)max_persist / (double)v.accessPolicyWindow.num_bytes);
-            v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-            v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-            if (cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &v) ==
-                cudaSuccess) {
-                  st = stream;
-                  active = true;
-            }
-            cudaGetLastError();
-      }
-      ~XWindow() {
-            if (!active)
-                  return;
-            cudaStreamAttrValue v{};
-            v.accessPolicyWindow.num_bytes = 0;
-            cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v);
-            cudaGetLastError();
-      }
-};
+// (An L2 access-policy window that pins part of a large x was tried and removed: reserving
+// the persisting carve-out shrinks the L2 left for everything else -- C2 dropped from 97 % to
+// 89 % of peak -- and C3/C4, whose gathers it was meant to help, did not move at all:
+// profiles/r1_kbench_c3_l2window_{on,off}.txt.  The per-load evict_last / evict_first
+// policies are what the kernels use.)
 
 } // namespace
 
@@ -582,7 +543,6 @@ int csr_run(spmv_b200_csr *h, int kernel, int wpb, long long row0, long long row
             return fail(-EINVAL, "null CSR handle");
       wpb = clamp_wpb(wpb);
       CsrArgs a{h, d_x, d_y, push, as_stream(stream), 32 * wpb};
-      XWindow xwin(d_x, h->N, a.st);
       bool any = false;
       for (auto &sg : h->segs) {
             if (sg.r0 < row0 || sg.r1 > row1)
@@ -1015,7 +975,6 @@ int hll_run(spmv_b200_hll *h, int kernel, int wpb, const double *d_x, double *d_
             return 0;
       wpb = clamp_wpb(wpb);
       cudaStream_t st = as_stream(stream);
-      XWindow xwin(d_x, h->N, st);
       const int threads = 32 * wpb;
       const int grid = blocks_for(h->n_hacks * 32, threads);
       switch (kernel) {
@@ -1363,8 +1322,6 @@ extern "C" int spmv_b200_set_knob(const char *key, int value) {
             g_knobs.force_wide = value;
       else if (!strcmp(key, "adaptive_direct"))
             g_knobs.adaptive_direct = value;
-      else if (!strcmp(key, "x_persist"))
-            g_knobs.x_persist = value;
       else
             return fail(-EINVAL, "unknown knob %s", key);
       return 0;
