@@ -65,7 +65,12 @@ def run(args):
     torch.cuda.synchronize()
     t_build = time.time() - t_build
     kernel = args.kernel if args.kernel is not None else 4
-    mode = os.environ.get("SPMV_B200_EXCHANGE", "push")
+    # Exchange mode.  "nccl" (batched isend/irecv on a high-priority side stream, overlapping
+    # the interior rows) is the default: measured 0.1181 / 0.1214 / 0.1251 ms per step at
+    # N = 2 / 4 / 8 (N=1: 0.1142).  "push" (halo stored into the neighbour's HBM from the SpMV
+    # epilogue + signal/wait kernels) matches it at N = 2 and 4 and on the 512^3 case at N = 8,
+    # but its weak-scaling run at N = 8 is not yet understood (profiles/r1_bench_N8_weak_push*).
+    mode = os.environ.get("SPMV_B200_EXCHANGE", "nccl")
 
     x0 = torch.from_numpy(x0_slice(r0, r1)).to(device)
     it = D.DistSpMV(dist, shard, plan, x0, device, mode=mode, kernel=kernel, wpb=args.wpb)
@@ -130,7 +135,9 @@ def run(args):
     # no host synchronisation in between: the ranks leave the host barrier up to a few ms
     # apart, and the first steps absorb that skew on the device (each rank's wait kernel
     # paces it to its neighbours) instead of charging it to the timed region.
-    warm = args.warmup + (args.warmup % 2)
+    # push mode lets a rank drift one step ahead per hop, so the skew needs ~world steps to drain
+    warm = max(args.warmup, world + 4)
+    warm += warm % 2
     it.run(warm)
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()

@@ -1371,7 +1371,8 @@ __global__ void wait_kernel(const unsigned long long *epoch, PeerSlots mine,
                         atomicExch(error, 1 + i);
                         return;
                   }
-                  __nanosleep(64);
+                  // plain polling: __nanosleep() rounds up to a scheduler quantum that is
+                  // longer than a whole SpMV step of the 128^3 slab
             }
       }
 }

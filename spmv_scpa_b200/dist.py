@@ -267,7 +267,7 @@ class DistSpMV:
             # every neighbour has finished the boundary rows of the previous step: its
             # pushes into X[src] have landed and it no longer reads the halo of X[dst]
             if L.b200.spmv_b200_wait_peers(C.c_void_p(self._epoch.data_ptr()), n, self._my_slots,
-                                           1 << 21, C.c_void_p(self._err.data_ptr()), st):
+                                           1 << 24, C.c_void_p(self._err.data_ptr()), st):
                 raise RuntimeError(L.last_error())
             for r0, r1, _ in boundary:
                 push = []
