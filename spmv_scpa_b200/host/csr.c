@@ -7,7 +7,9 @@
  *   bench_csr_cuda_*   :382-415  (forward to libspmv_b200, cuda_csr.h)
  *
  * The loader reads the entry section of the file ONCE into memory and
- * tokenises it there (the reference runs fscanf over the file twice); the
+ * tokenises it there -- in parallel over line-aligned chunks when the file is
+ * large and regular, with a sequential walk as the fallback and as the
+ * arbiter of every error (the reference runs fscanf over the file twice); the
  * arithmetic that decides the result -- strtol for indices, strtod for
  * values, both correctly rounded like fscanf -- and the order in which
  * entries land in each row (file order; a symmetric off-diagonal (i,j) is
@@ -99,6 +101,129 @@ static int read_double(struct cursor *c, double *out) {
       return 0;
 }
 
+/* ---- entry section: sequential reference walk ---------------------------
+ * Parses up to n_decl entries in file order.  Returns the number of entries
+ * accepted; *err is 0, or the errno of the first problem (-EIO for a token
+ * that does not convert / early end, -ERANGE for an index outside M x N) --
+ * the same first-problem-wins order as the reference's pass 1
+ * (src/csr.c:68-95). */
+static size_t parse_entries_serial(const char *text, size_t n_decl, int pattern,
+                                   int M, int N, int *ei, int *ej, double *ev,
+                                   int *err) {
+      struct cursor cur = {text};
+      *err = 0;
+      for (size_t e = 0; e < n_decl; ++e) {
+            int i, j;
+            double v = 1.0;
+            if (read_int(&cur, &i) || read_int(&cur, &j) ||
+                (!pattern && read_double(&cur, &v))) {
+                  *err = -EIO;
+                  return e;
+            }
+            --i, --j;
+            if (i < 0 || i >= M || j < 0 || j >= N) {
+                  *err = -ERANGE;
+                  return e;
+            }
+            ei[e] = i, ej[e] = j;
+            if (!pattern)
+                  ev[e] = v;
+      }
+      return n_decl;
+}
+
+/* ---- entry section: parallel walk ---------------------------------------
+ * The text is cut at line ends into one chunk per thread.  A first sweep
+ * counts white-space separated tokens per chunk; if every chunk starts on an
+ * entry boundary (token index divisible by the tokens per entry) the chunks
+ * are parsed independently, each writing its entries at their global index.
+ * Anything unusual -- a chunk not aligned to entries, a number glued to the
+ * next token (which fscanf would split differently), any conversion error --
+ * makes the function return -1 and the caller falls back to the sequential
+ * walk, so the result is always the one the reference's fscanf loop gives. */
+static int parse_entries_parallel(const char *text, size_t len, size_t n_decl,
+                                  int pattern, int M, int N, int *ei, int *ej,
+                                  double *ev) {
+#ifndef _OPENMP
+      (void)text, (void)len, (void)n_decl, (void)pattern, (void)M, (void)N;
+      (void)ei, (void)ej, (void)ev;
+      return -1;
+#else
+      int nt = omp_get_max_threads();
+      if (nt > 64)
+            nt = 64;
+      if (nt < 2 || len < ((size_t)1 << 20))
+            return -1;
+      const int tpe = pattern ? 2 : 3;
+      size_t cut[65], tok[65];
+      cut[0] = 0;
+      for (int t = 1; t < nt; ++t) {
+            size_t p = len / nt * t;
+            if (p < cut[t - 1])
+                  p = cut[t - 1];
+            while (p < len && text[p] != '\n')
+                  ++p;
+            cut[t] = p < len ? p + 1 : len;
+      }
+      cut[nt] = len;
+
+      int bad = 0;
+#pragma omp parallel num_threads(nt) reduction(| : bad)
+      {
+            const int t = omp_get_thread_num();
+            if (omp_get_num_threads() != nt)
+                  bad |= 1; /* the runtime granted a smaller team: chunks would go unparsed */
+            size_t n = 0;
+            int in_tok = 0;
+            for (size_t p = cut[t]; p < cut[t + 1]; ++p) {
+                  const int sp = isspace((unsigned char)text[p]) || text[p] == '\0';
+                  n += (!sp && !in_tok);
+                  in_tok = !sp;
+            }
+            tok[t + 1] = n;
+#pragma omp barrier
+#pragma omp single
+            {
+                  tok[0] = 0;
+                  for (int k = 0; k < nt; ++k)
+                        tok[k + 1] += tok[k];
+            }
+            if (tok[t] % tpe != 0) {
+                  bad |= 1;
+            } else {
+                  size_t e = tok[t] / tpe;
+                  const size_t e_end = tok[t + 1] / tpe; /* whole entries in this chunk */
+                  struct cursor cur = {text + cut[t]};
+                  const char *stop_at = text + cut[t + 1];
+                  for (; e < e_end && e < n_decl && !bad; ++e) {
+                        int i, j;
+                        double v = 1.0;
+                        if (read_int(&cur, &i) || !(isspace((unsigned char)*cur.p)) ||
+                            read_int(&cur, &j) ||
+                            (!pattern && (!isspace((unsigned char)*cur.p) ||
+                                          read_double(&cur, &v))) ||
+                            !(isspace((unsigned char)*cur.p) || *cur.p == '\0') ||
+                            cur.p > stop_at) {
+                              bad |= 1;
+                              break;
+                        }
+                        --i, --j;
+                        if (i < 0 || i >= M || j < 0 || j >= N) {
+                              bad |= 1; /* let the sequential walk pick the errno */
+                              break;
+                        }
+                        ei[e] = i, ej[e] = j;
+                        if (!pattern)
+                              ev[e] = v;
+                  }
+            }
+      }
+      if (bad || tok[nt] / tpe < n_decl) /* short file: sequential walk reports it */
+            return -1;
+      return 0;
+#endif
+}
+
 sparse_csr *io_load_csr(const char *path) {
       char name[MAX_NAME];
       MM_typecode tc;
@@ -108,7 +233,7 @@ sparse_csr *io_load_csr(const char *path) {
       char *text = NULL;
       int *ei = NULL, *ej = NULL; /* parsed coordinates, file order */
       double *ev = NULL;
-      int *fill = NULL; /* per-row insertion cursor */
+      int *fill = NULL; /* per-row counts, then insertion cursors */
       int *IRP = NULL, *JA = NULL;
       double *AS = NULL;
       sparse_csr *A = NULL;
@@ -134,36 +259,26 @@ sparse_csr *io_load_csr(const char *path) {
       ei = malloc((n_decl ? n_decl : 1) * sizeof *ei);
       ej = malloc((n_decl ? n_decl : 1) * sizeof *ej);
       ev = pattern ? NULL : malloc((n_decl ? n_decl : 1) * sizeof *ev);
-      fill = calloc(M > 0 ? (size_t)M : 1, sizeof *fill);
+      fill = calloc(M > 0 ? (size_t)M + 1 : 2, sizeof *fill);
       if (!text || !ei || !ej || (!pattern && !ev) || !fill) {
             err = -ENOMEM;
             goto out;
       }
 
-      /* Pass over the text: parse, range-check, count per row.  The first
-       * problem met in file order decides the error code, as in the
-       * reference's first pass (src/csr.c:68-95). */
+      /* parse (parallel when the file is large and regular, else sequential) */
+      if (parse_entries_parallel(text, text_len, n_decl, pattern, M, N, ei, ej,
+                                 ev) != 0) {
+            parse_entries_serial(text, n_decl, pattern, M, N, ei, ej, ev, &err);
+            if (err)
+                  goto out;
+      }
+
+      /* count per row (a symmetric off-diagonal also counts for its mirror) */
       long total = 0;
-      struct cursor cur = {text};
       for (size_t e = 0; e < n_decl; ++e) {
-            int i, j;
-            double v = 1.0;
-            if (read_int(&cur, &i) || read_int(&cur, &j) ||
-                (!pattern && read_double(&cur, &v))) {
-                  err = -EIO;
-                  goto out;
-            }
-            --i, --j;
-            if (i < 0 || i >= M || j < 0 || j >= N) {
-                  err = -ERANGE;
-                  goto out;
-            }
-            ei[e] = i, ej[e] = j;
-            if (!pattern)
-                  ev[e] = v;
-            ++fill[i], ++total;
-            if (symmetric && i != j)
-                  ++fill[j], ++total;
+            ++fill[ei[e]], ++total;
+            if (symmetric && ei[e] != ej[e])
+                  ++fill[ej[e]], ++total;
       }
 
       IRP = aligned_malloc(((size_t)M + 1) * sizeof *IRP);
@@ -172,10 +287,8 @@ sparse_csr *io_load_csr(const char *path) {
             goto out;
       }
       IRP[0] = 0;
-      for (int r = 0; r < M; ++r) {
+      for (int r = 0; r < M; ++r)
             IRP[r + 1] = IRP[r] + fill[r];
-            fill[r] = IRP[r]; /* becomes the write cursor of row r */
-      }
 
       JA = aligned_malloc((size_t)total * sizeof *JA);
       AS = aligned_malloc((size_t)total * sizeof *AS);
@@ -184,14 +297,55 @@ sparse_csr *io_load_csr(const char *path) {
             goto out;
       }
 
-      for (size_t e = 0; e < n_decl; ++e) {
-            const int i = ei[e], j = ej[e];
-            const double v = pattern ? 1.0 : ev[e];
-            int k = fill[i]++;
-            JA[k] = j, AS[k] = v;
-            if (symmetric && i != j) {
-                  k = fill[j]++;
-                  JA[k] = i, AS[k] = v;
+      /* Scatter in file order.  Rows are dealt to threads in contiguous ranges
+       * of ~equal entry count; every thread walks ALL entries and keeps those
+       * of its rows, so the order inside a row is the file order whatever the
+       * thread count (an entry, then its mirror). */
+      {
+#ifdef _OPENMP
+            int nt = total > (1 << 20) ? omp_get_max_threads() : 1;
+#else
+            int nt = 1;
+#endif
+            if (nt > 64)
+                  nt = 64;
+            int row_cut[65];
+            row_cut[0] = 0;
+            for (int t = 1; t < nt; ++t) {
+                  const long want = total / nt * t;
+                  int lo = row_cut[t - 1], hi = M;
+                  while (lo < hi) { /* first row whose offset reaches `want` */
+                        const int mid = lo + (hi - lo) / 2;
+                        if (IRP[mid] < want)
+                              lo = mid + 1;
+                        else
+                              hi = mid;
+                  }
+                  row_cut[t] = lo;
+            }
+            row_cut[nt] = M;
+            for (int r = 0; r < M; ++r)
+                  fill[r] = IRP[r]; /* write cursor of row r */
+#pragma omp parallel num_threads(nt)
+            {
+#ifdef _OPENMP
+                  const int t = omp_get_thread_num();
+#else
+                  const int t = 0;
+#endif
+                  const int r_lo = row_cut[t], r_hi = row_cut[t + 1];
+                  for (size_t e = 0; e < n_decl; ++e) {
+                        const int i = ei[e], j = ej[e];
+                        const double v = pattern ? 1.0 : ev[e];
+                        if (i >= r_lo && i < r_hi) {
+                              const int k = fill[i]++;
+                              JA[k] = j, AS[k] = v;
+                        }
+                        if (symmetric && i != j && j >= r_lo && j < r_hi) {
+                              const int k = fill[j]++;
+                              JA[k] = i, AS[k] = v;
+                        }
+                  }
             }
       }
 

@@ -142,3 +142,73 @@ def test_product_loader_vs_reference_live(sp, O, have_ref, tmp_path):
         assert np.array_equal(A.JA, want[3])
         assert np.array_equal(bits(A.AS), bits(want[4]))
         assert A.name == want[5]
+
+
+# ------------------------------------------------------- large files: parallel parse path --
+def _write_big(path, field, sym, M, N, nnz, rng, layout="lines"):
+    i = rng.integers(1, M + 1, nnz)
+    j = rng.integers(1, N + 1, nnz)
+    if sym != "general":
+        i, j = np.maximum(i, j), np.minimum(i, j)
+    v = rng.normal(0, 1e3, nnz)
+    with open(path, "w") as f:
+        f.write(f"%%MatrixMarket matrix coordinate {field} {sym}\n% big\n{M} {N} {nnz}\n")
+        if layout == "lines":          # one entry per line: the parallel path
+            if field == "pattern":
+                f.write("".join(f"{a} {b}\n" for a, b in zip(i, j)))
+            else:
+                f.write("".join(f"{a} {b} {c:.17g}\n" for a, b, c in zip(i, j, v)))
+        elif layout == "token_per_line":  # every token on its own line: chunks not entry-aligned
+            f.write("".join(f"{a}\n{b}\n{c:.17g}\n" for a, b, c in zip(i, j, v)))
+        elif layout == "two_per_line":
+            it = iter(zip(i, j, v))
+            f.write("".join(f"{a} {b} {c:.17g} {d} {e} {g:.17g}\n"
+                            for (a, b, c), (d, e, g) in zip(it, it)))
+    return path
+
+
+@pytest.mark.parametrize("field,sym,layout", [("real", "general", "lines"), ("real", "symmetric", "lines"),
+                                              ("pattern", "general", "lines"), ("pattern", "symmetric", "lines"),
+                                              ("real", "general", "token_per_line"),
+                                              ("real", "general", "two_per_line")])
+def test_large_file_parallel_parse_bit_exact(sp, O, tmp_path, field, sym, layout):
+    """> 1 MB of entries takes the chunked parallel parser (or its sequential fallback for
+    layouts a chunk cannot be aligned to); either way the arrays equal the fscanf walk of the
+    oracle port, which is pinned to the reference."""
+    rng = np.random.default_rng(99)
+    M, N, nnz = 5000, (5000 if sym != "general" else 3000), 120000
+    p = _write_big(str(tmp_path / "big.mtx"), field, sym, M, N, nnz, rng, layout)
+    assert os.path.getsize(p) > (1 << 20) or field == "pattern"
+    want = O.load_mtx(p)
+    if O.ref_available():
+        ref = O.ref_load_mtx(p)
+        for a, b in zip(want[2:5], ref[2:5]):
+            assert np.array_equal(a, b)
+    A = sp.io_load_csr(p)
+    assert (A.M, A.N) == (want[0], want[1])
+    assert np.array_equal(A.IRP, want[2])
+    assert np.array_equal(A.JA, want[3])
+    assert np.array_equal(bits(A.AS), bits(want[4]))
+
+
+def test_large_file_errors_keep_reference_order(sp, O, tmp_path):
+    """An out-of-range index deep inside a big file, and a truncated big file: same errno as
+    the sequential reference walk."""
+    rng = np.random.default_rng(5)
+    p = _write_big(str(tmp_path / "e.mtx"), "real", "general", 4000, 4000, 100000, rng)
+    lines = open(p).read().splitlines()
+    bad = list(lines)
+    bad[70000] = "4001 1 1.0"           # ERANGE at entry ~70000
+    bad[90000] = "x y z"                # a later EIO must not win
+    q = str(tmp_path / "erange.mtx")
+    open(q, "w").write("\n".join(bad) + "\n")
+    for loader in (sp.io_load_csr, O.load_mtx):
+        with pytest.raises(OSError) as ei:
+            loader(q)
+        assert ei.value.errno == errno.ERANGE
+    q2 = str(tmp_path / "short.mtx")
+    open(q2, "w").write("\n".join(lines[:50000]) + "\n")
+    for loader in (sp.io_load_csr, O.load_mtx):
+        with pytest.raises(OSError) as ei:
+            loader(q2)
+        assert ei.value.errno == errno.EIO
