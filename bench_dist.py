@@ -139,6 +139,12 @@ def run(args):
     warm = max(args.warmup, world + 4)
     warm += warm % 2
     it.run(warm)
+    # device-side rendezvous right before the start event: the first graph launch costs a
+    # different number of milliseconds on every rank, and in push mode a rank may run one step
+    # ahead per hop, so without it the early ranks' timed region would include the late ranks'
+    # start-up.  (Stream-ordered: the compute stream waits for the all-reduce, not the host.)
+    sync_word = torch.zeros(1, device=device)
+    dist.all_reduce(sync_word)
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
     it.run(args.steps)
