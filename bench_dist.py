@@ -65,12 +65,12 @@ def run(args):
     torch.cuda.synchronize()
     t_build = time.time() - t_build
     kernel = args.kernel if args.kernel is not None else 4
-    # Exchange mode.  "nccl" (batched isend/irecv on a high-priority side stream, overlapping
-    # the interior rows) is the default: measured 0.1181 / 0.1214 / 0.1251 ms per step at
-    # N = 2 / 4 / 8 (N=1: 0.1142).  "push" (halo stored into the neighbour's HBM from the SpMV
-    # epilogue + signal/wait kernels) matches it at N = 2 and 4 and on the 512^3 case at N = 8,
-    # but its weak-scaling run at N = 8 is not yet understood (profiles/r1_bench_N8_weak_push*).
-    mode = os.environ.get("SPMV_B200_EXCHANGE", "nccl")
+    # Exchange mode.  "push" (default): the boundary-row kernel stores the halo into the
+    # neighbour's HBM from its epilogue, signal/wait kernels order the steps -- no collective on
+    # the step path.  "nccl": batched isend/irecv on a high-priority side stream overlapping
+    # the interior rows.  Measured ms per step at N = 2 / 4 / 8 (N=1: 0.1142):
+    #   push 0.1186 / 0.1232 / 0.1238     nccl 0.1181 / 0.1214 / 0.1251     (profiles/r1_bench_N*)
+    mode = os.environ.get("SPMV_B200_EXCHANGE", "push")
 
     x0 = torch.from_numpy(x0_slice(r0, r1)).to(device)
     it = D.DistSpMV(dist, shard, plan, x0, device, mode=mode, kernel=kernel, wpb=args.wpb)
