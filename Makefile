@@ -21,7 +21,7 @@ CFLAGS  := -std=gnu99 -O3 -march=x86-64-v3 -fopenmp -fPIC -Wall -Wextra -Wno-unu
 NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -ccbin $(CXX) -Xcompiler -fPIC,-Wall,-fopenmp \
            -Xptxas -v --expt-relaxed-constexpr $(INC) -I$(PKG)/csrc
 
-HOST_SRC := $(addprefix $(PKG)/host/,mmio.c utils.c vector.c logger.c csr.c hll.c gen.c)
+HOST_SRC := $(addprefix $(PKG)/host/,mmio.c support.c logger.c csr.c hll.c gen.c)
 CUDA_SRC := $(PKG)/csrc/spmv_b200.cu
 CUDA_DEP := $(wildcard $(PKG)/csrc/*.cuh) $(wildcard include/*.h)
 

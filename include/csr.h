@@ -1,9 +1,8 @@
-/* csr.h -- host CSR container, Matrix Market loader and CSR benchmarks.
+/* csr.h -- host CSR matrix, its Matrix Market loader, and the CSR benchmark entry points.
  *
- * Drop-in for the reference's include/csr.h: struct layout (:7-13,
- * sizeof == 104 on x86-64), init_csr (:15-24) and every prototype (:29-49)
- * keep their meaning.  Indices are 0-based int32, values FP64, IRP has M+1
- * entries, within-row order is the order of appearance in the .mtx file.
+ * Binary-compatible with the reference (include/csr.h:7-13: 104 bytes on x86-64; prototypes
+ * :29-49).  Conventions: 0-based int32 indices, FP64 values, IRP has M+1 entries, entries of a
+ * row keep the order in which the .mtx file listed them (duplicates and explicit zeros kept).
  */
 #ifndef SPMV_B200_CSR_H
 #define SPMV_B200_CSR_H
@@ -17,53 +16,54 @@ extern "C" {
 #endif
 
 typedef struct sparse_matrix_csr {
-      char name[MAX_NAME]; /* basename of the .mtx without extension */
-      int M, N, NZ;        /* rows, cols, stored entries */
-      int *IRP;            /* [M+1] row pointers */
-      int *JA;             /* [NZ] column indices */
-      double *AS;          /* [NZ] values */
+    char name[MAX_NAME]; /* file name without directory and ".mtx"        */
+    int M, N, NZ;        /* rows, columns, stored entries                  */
+    int *IRP;            /* row offsets, M + 1 of them                     */
+    int *JA;             /* column of every entry                          */
+    double *AS;          /* value of every entry                           */
 } sparse_csr;
 
-/* Wrap caller-owned arrays in a sparse_csr (no copy). */
-static inline void init_csr(sparse_csr *A, const char *name, int M, int N,
-                            int NZ, int *IRP, int *JA, double *AS) {
-      snprintf(A->name, sizeof A->name, "%s", name);
-      A->M = M, A->N = N, A->NZ = NZ;
-      A->IRP = IRP, A->JA = JA, A->AS = AS;
+/* Describe arrays the caller already owns; nothing is copied or allocated. */
+static inline void init_csr(sparse_csr *dst, const char *name, int rows, int cols, int nnz,
+                            int *irp, int *ja, double *as) {
+    snprintf(dst->name, sizeof dst->name, "%s", name);
+    dst->M = rows;
+    dst->N = cols;
+    dst->NZ = nnz;
+    dst->IRP = irp;
+    dst->JA = ja;
+    dst->AS = as;
 }
 
-/* Matrix Market coordinate {real,pattern} x {general,symmetric,...} -> CSR.
- * Failure is an ERR_PTR(-errno): -EINVAL (unsupported banner / size line),
- * -ERANGE (index outside the declared shape), -EIO (short file), -ENOMEM,
- * or -errno from fopen (reference: src/csr.c:31-171). */
-sparse_csr *io_load_csr(const char *path);
+/* "matrix coordinate {real|pattern} {general|symmetric|...}" file -> CSR.
+ * On failure the result satisfies IS_ERR() and PTR_ERR() is
+ *   -EINVAL  banner / size line not acceptable (integer, complex, array, ...)
+ *   -ERANGE  an index outside the declared shape
+ *   -EIO     fewer entries than declared, or a token that is not a number
+ *   -ENOMEM, or -errno of fopen()
+ * exactly as the reference loader decides (src/csr.c:31-171). */
+sparse_csr *io_load_csr(const char *mtx_path);
 
-/* Frees the three arrays and the struct; NULL is ignored. */
-void csr_free(sparse_csr *A);
+/* releases the three arrays and the struct (NULL is fine) */
+void csr_free(sparse_csr *matrix);
 
-/* CPU paths (serial / OpenMP).  They exist so the CLI keeps writing
- * serial.csv and omp.csv; they are never used by the GPU path. */
-int bench_csr_serial(const sparse_csr *A, const double *x, bench *out);
-int bench_csr_omp_guided(const sparse_csr *A, const double *x, bench_omp *out);
-int bench_csr_omp_nnz_balancing(const sparse_csr *A, const double *x,
-                                bench_omp *out);
+/* ---- benchmarks: each allocates y, runs one variant, fills duration / GFLOP/s ------------
+ * CPU variants (kept so the driver still writes serial.csv / omp.csv; never a fallback for
+ * the GPU path): */
+int bench_csr_serial(const sparse_csr *matrix, const double *x, bench *result);
+int bench_csr_omp_guided(const sparse_csr *matrix, const double *x, bench_omp *result);
+int bench_csr_omp_nnz_balancing(const sparse_csr *matrix, const double *x, bench_omp *result);
 
-/* GPU paths: set out->warps_per_block, call; out->bench is filled with the
- * kernel time (ms), GFLOP/s and a freshly allocated y.  Each forwards to the
- * matching csr_spmv_cuda_* entry of libspmv_b200 (cuda_csr.h). */
-int bench_csr_cuda_thread_row(const sparse_csr *A, const double *x,
-                              bench_cuda *out);
-int bench_csr_cuda_warp_row(const sparse_csr *A, const double *x,
-                            bench_cuda *out);
-int bench_csr_cuda_halfwarp_row(const sparse_csr *A, const double *x,
-                                bench_cuda *out);
-int bench_csr_cuda_block_row(const sparse_csr *A, const double *x,
-                             bench_cuda *out);
-int bench_csr_cuda_halfwarp_row_text(const sparse_csr *A, const double *x,
-                                     bench_cuda *out);
+/* GPU variants: result->warps_per_block is an input.  They forward to the csr_spmv_cuda_*
+ * symbol of the same suffix in libspmv_b200 (cuda_csr.h lists the kernel behind each). */
+#define SPMV_CSR_CUDA_VARIANTS(X) \
+    X(thread_row) X(warp_row) X(halfwarp_row) X(block_row) X(halfwarp_row_text)
+#define SPMV_DECLARE(suffix) \
+    int bench_csr_cuda_##suffix(const sparse_csr *matrix, const double *x, bench_cuda *result);
+SPMV_CSR_CUDA_VARIANTS(SPMV_DECLARE)
+#undef SPMV_DECLARE
 
 #ifdef __cplusplus
 }
 #endif
-
 #endif /* SPMV_B200_CSR_H */

@@ -34,16 +34,14 @@ extern "C" {
 
 void set_csr_warps_per_block(int wppb);
 
-double csr_spmv_cuda_thread_row(const sparse_csr *A, const double *x, double *y,
-                                void *_unused);
-double csr_spmv_cuda_warp_row(const sparse_csr *A, const double *x, double *y,
-                              void *_unused);
-double csr_spmv_cuda_halfwarp_row(const sparse_csr *A, const double *x,
-                                  double *y, void *_unused);
-double csr_spmv_cuda_block_row(const sparse_csr *A, const double *x, double *y,
-                               void *_unused);
-double csr_spmv_cuda_halfwarp_row_text(const sparse_csr *A, const double *x,
-                                       double *y, void *_unused);
+/* one prototype per variant of SPMV_CSR_CUDA_VARIANTS (see csr.h):
+ *   double csr_spmv_cuda_<variant>(const sparse_csr *matrix, const double *x_host,
+ *                                    double *y_host, void *unused);                  */
+#define SPMV_DECLARE(suffix)                                                          \
+    double csr_spmv_cuda_##suffix(const sparse_csr *matrix, const double *x_host,        \
+                                    double *y_host, void *unused);
+SPMV_CSR_CUDA_VARIANTS(SPMV_DECLARE)
+#undef SPMV_DECLARE
 
 #ifdef __cplusplus
 }

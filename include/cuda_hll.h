@@ -30,14 +30,14 @@ extern "C" {
 
 void set_hll_warps_per_block(int wppb);
 
-double hll_spmv_cuda_threads_row_major(const sparse_hll *H, const double *x,
-                                       double *y, void *_unused);
-double hll_spmv_cuda_threads_col_major(const sparse_hll *H, const double *x,
-                                       double *y, void *_unused);
-double hll_spmv_cuda_warp_block(const sparse_hll *H, const double *x, double *y,
-                                void *_unused);
-double hll_spmv_cuda_halfwarp_row(const sparse_hll *H, const double *x,
-                                  double *y, void *_unused);
+/* one prototype per variant of SPMV_HLL_CUDA_VARIANTS (see hll.h):
+ *   double hll_spmv_cuda_<variant>(const sparse_hll *matrix, const double *x_host,
+ *                                    double *y_host, void *unused);                  */
+#define SPMV_DECLARE(suffix)                                                          \
+    double hll_spmv_cuda_##suffix(const sparse_hll *matrix, const double *x_host,        \
+                                    double *y_host, void *unused);
+SPMV_HLL_CUDA_VARIANTS(SPMV_DECLARE)
+#undef SPMV_DECLARE
 
 #ifdef __cplusplus
 }

@@ -1,11 +1,14 @@
-/* hll.h -- hacked-ELLPACK (HLL) host container and packer, hack = 32 rows.
+/* hll.h -- HLL ("hacked ELLPACK") host matrix: the rows are cut into hacks of 32, every hack
+ * is an ELLPACK block padded to its own widest row.
  *
- * Drop-in for the reference's include/hll.h: ellpack_block (:13-18,
- * sizeof == 32), sparse_hll (:31-37, sizeof == 96), init helpers (:20-28,
- * :39-48) and prototypes (:54-70).  A hack stores `M` consecutive rows padded
- * to the widest one (`max_NZ`); padding is JA = -1 / AS = 0.0; the layout is
- * row-major (slot = i*max_NZ + j) or column-major (slot = j*M + i, stride =
- * rows of THIS hack, so the last hack may use a stride < 32).
+ * Binary-compatible with the reference (include/hll.h:13-18 ellpack_block = 32 bytes,
+ * :31-37 sparse_hll = 96 bytes; prototypes :54-70).  Inside a hack of `M` rows and width
+ * `max_NZ`, entry j of row i sits at
+ *      i * max_NZ + j     row-major
+ *      j * M + i          column-major   (stride = rows of THIS hack: the last hack of a
+ *                                         matrix whose row count is not a multiple of 32 is
+ *                                         narrower)
+ * and every unused slot holds JA = -1, AS = 0.0.
  */
 #ifndef SPMV_B200_HLL_H
 #define SPMV_B200_HLL_H
@@ -23,60 +26,61 @@ extern "C" {
 #define HACK_SIZE 32
 
 typedef struct {
-      int M, N, NZ; /* rows in this hack, matrix cols, real entries */
-      int max_NZ;   /* padded width */
-      int *JA;      /* [M*max_NZ] */
-      double *AS;   /* [M*max_NZ] */
+    int M, N, NZ; /* rows of this hack, columns of the matrix, real entries in the hack */
+    int max_NZ;   /* slots per row                                                        */
+    int *JA;      /* M * max_NZ column indices                                            */
+    double *AS;   /* M * max_NZ values                                                    */
 } ellpack_block;
 
-static inline void init_ellpack_block(ellpack_block *blk, int M, int N, int NZ,
-                                      int max_NZ) {
-      blk->M = M, blk->N = N, blk->NZ = NZ;
-      blk->max_NZ = max_NZ;
-      blk->JA = NULL;
-      blk->AS = NULL;
-}
-
 typedef struct {
-      char name[MAX_NAME];
-      int M, N, NZ;
-      int hack_size;  /* always HACK_SIZE */
-      int num_blocks; /* ceil(M / HACK_SIZE) */
-      ellpack_block *blocks;
+    char name[MAX_NAME];
+    int M, N, NZ;
+    int hack_size;  /* HACK_SIZE                       */
+    int num_blocks; /* (M + HACK_SIZE - 1) / HACK_SIZE */
+    ellpack_block *blocks;
 } sparse_hll;
 
-static inline void init_hll(sparse_hll *H, const char *name, int M, int N,
-                            int NZ, int num_blocks) {
-      snprintf(H->name, sizeof H->name, "%s", name);
-      H->M = M, H->N = N, H->NZ = NZ;
-      H->hack_size = HACK_SIZE;
-      H->num_blocks = num_blocks;
-      H->blocks = NULL;
+static inline void init_ellpack_block(ellpack_block *dst, int rows, int cols, int entries,
+                                      int width) {
+    dst->M = rows;
+    dst->N = cols;
+    dst->NZ = entries;
+    dst->max_NZ = width;
+    dst->JA = NULL;
+    dst->AS = NULL;
 }
 
-/* CSR -> HLL, bit-exact with the reference packer (src/hll.c:19-95).
- * Returns ERR_PTR(-ENOMEM) on allocation failure. */
-sparse_hll *csr_to_hll(const sparse_csr *A, bool is_col_major);
+static inline void init_hll(sparse_hll *dst, const char *name, int rows, int cols, int nnz,
+                            int hacks) {
+    snprintf(dst->name, sizeof dst->name, "%s", name);
+    dst->M = rows;
+    dst->N = cols;
+    dst->NZ = nnz;
+    dst->hack_size = HACK_SIZE;
+    dst->num_blocks = hacks;
+    dst->blocks = NULL;
+}
 
-void hll_free(sparse_hll *H);
+/* Pack a CSR matrix; every field of every hack equals what the reference packer produces
+ * (src/hll.c:19-95).  IS_ERR() result with -ENOMEM when memory runs out. */
+sparse_hll *csr_to_hll(const sparse_csr *matrix, bool column_major);
+void hll_free(sparse_hll *matrix);
 
-int bench_hll_serial(const sparse_hll *H, const double *x, bench *out);
-int bench_hll_omp(const sparse_hll *H, const double *x, bench_omp *out);
+/* CPU variants (row-major hacks; padding skipped by testing JA == -1) */
+int bench_hll_serial(const sparse_hll *matrix, const double *x, bench *result);
+int bench_hll_omp(const sparse_hll *matrix, const double *x, bench_omp *result);
 
-/* GPU paths; the layout of H is implied by the entry point: row-major for
- * _threads_row_major and _halfwarp_row, column-major for the other two
- * (reference: src/main.c:324-325). */
-int bench_hll_cuda_threads_row_major(const sparse_hll *H, const double *x,
-                                     bench_cuda *out);
-int bench_hll_cuda_threads_col_major(const sparse_hll *H, const double *x,
-                                     bench_cuda *out);
-int bench_hll_cuda_warp_block(const sparse_hll *H, const double *x,
-                              bench_cuda *out);
-int bench_hll_cuda_halfwarp_row(const sparse_hll *H, const double *x,
-                                bench_cuda *out);
+/* GPU variants.  The entry point implies the host layout it is given (reference
+ * src/main.c:324-325): row-major for threads_row_major and halfwarp_row, column-major for
+ * threads_col_major and warp_block. */
+#define SPMV_HLL_CUDA_VARIANTS(X) \
+    X(threads_row_major) X(threads_col_major) X(warp_block) X(halfwarp_row)
+#define SPMV_DECLARE(suffix) \
+    int bench_hll_cuda_##suffix(const sparse_hll *matrix, const double *x, bench_cuda *result);
+SPMV_HLL_CUDA_VARIANTS(SPMV_DECLARE)
+#undef SPMV_DECLARE
 
 #ifdef __cplusplus
 }
 #endif
-
 #endif /* SPMV_B200_HLL_H */

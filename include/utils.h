@@ -1,9 +1,7 @@
-/* utils.h -- shared constants, benchmark result records, small helpers.
+/* utils.h -- constants, benchmark records and helpers shared by the host layer.
  *
- * Mirrors the observable surface of the reference's include/utils.h:
- * constants (:12-18), bench / bench_omp / bench_cuda records (:32-47),
- * log_prog_usage / validation_vec_result / aligned_malloc (:61-77),
- * now() and compute_gflops() (:68-75).  Record layouts are ABI.
+ * The three records are ABI (reference include/utils.h:32-47): they are filled by the
+ * bench_* functions and passed BY VALUE to the logger.
  */
 #ifndef SPMV_B200_UTILS_H
 #define SPMV_B200_UTILS_H
@@ -13,75 +11,63 @@
 #include <stdio.h>
 #include <time.h>
 
+#include "spmv_errptr.h"
 #include "vector.h"
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-#define ALIGNMENT 64 /* host array alignment, bytes */
-#define MAX_NAME 64  /* matrix / bench name buffer */
-#define MAX_PATH 256 /* csv path buffer */
-
+enum {
+    ALIGNMENT = 64, /* bytes; every array the loader / packer hands out     */
+    MAX_NAME = 64,  /* matrix and bench name buffers                        */
+    MAX_PATH = 256  /* csv path buffer                                      */
+};
 #define ARRAY_SIZE(a) (sizeof(a) / sizeof((a)[0]))
 
-/* One timed SpMV: milliseconds, 2*nnz/t GFLOP/s and the produced y. */
+/* result of one timed y = A x */
 typedef struct benchmark_result {
-      double duration_ms;
-      double gflops;
-      vec data;
+    double duration_ms; /* kernel / loop time                                */
+    double gflops;      /* 2 nnz / time                                      */
+    vec data;           /* the y that was produced; the caller releases it   */
 } bench;
 
 typedef struct benchmark_omp {
-      bench bench;
-      char name[MAX_NAME]; /* "omp_nnz" | "omp_guided" */
-      int num_threads;
+    bench bench;
+    char name[MAX_NAME]; /* "omp_nnz" or "omp_guided" (csv column `bench`)   */
+    int num_threads;
 } bench_omp;
 
 typedef struct benchmark_cuda {
-      bench bench;
-      int warps_per_block;
+    bench bench;
+    int warps_per_block; /* in: CTA size knob; echoed into cuda.csv          */
 } bench_cuda;
 
-#define LOG_WARN(fmt, ...)                                                     \
-      do {                                                                     \
-            fprintf(stdout, "[WARN ] %s:%d: " fmt "\n", __FILE__, __LINE__,    \
-                    ##__VA_ARGS__);                                            \
-      } while (0)
-
-#define LOG_INFO(fmt, ...)                                                     \
-      do {                                                                     \
-            fprintf(stdout, "[INFO ] %s:%d: " fmt "\n", __FILE__, __LINE__,    \
-                    ##__VA_ARGS__);                                            \
-      } while (0)
-
-/* Spin up an OpenMP team once so the first timed region is not charged for
- * thread creation (reference: OMP_WARMUP, include/utils.h:20-30). */
+/* start an OpenMP team once so the first timed region does not pay for thread creation */
 void omp_warmup(int num_threads);
-#define OMP_WARMUP(nt) omp_warmup(nt)
+#define OMP_WARMUP(n) omp_warmup(n)
 
 void log_prog_usage(const char *prog);
-void print_result_vector(const vec res);
+void print_result_vector(const vec y);
 
-/* 0 when ||expected - res||_2 <= 0.1 and lengths match, else -1
- * (reference: src/utils.c:39-60; the `-d` gate of the CLI). */
-int validation_vec_result(const vec expected, const vec res);
+/* the `-d` gate: 0 when the lengths agree and ||expected - got||_2 <= 0.1, otherwise -1
+ * (reference src/utils.c:39-60) */
+int validation_vec_result(const vec expected, const vec got);
 
-/* posix_memalign(ALIGNMENT) or NULL. */
-void *aligned_malloc(size_t size);
+/* posix_memalign(ALIGNMENT); NULL on failure */
+void *aligned_malloc(size_t bytes);
 
-/* CPU time in milliseconds (clock()), as the serial paths of the reference. */
-static inline double now(void) {
-      return (double)clock() * 1e3 / (double)CLOCKS_PER_SEC;
-}
+/* process CPU time in milliseconds -- the clock of the serial paths */
+static inline double now(void) { return 1e3 * (double)clock() / (double)CLOCKS_PER_SEC; }
 
-/* 2*nnz flop in `duration` ms -> GFLOP/s; non-positive time -> 0. */
-static inline double compute_gflops(double duration, int nnz) {
-      return duration > 0.0 ? (2.0 * (double)nnz) / (duration * 1e6) : 0.0;
+/* GFLOP/s of 2*nnz flop done in `ms` milliseconds; a failed run (ms <= 0) scores 0 */
+static inline double compute_gflops(double ms, int nnz) {
+    if (!(ms > 0.0))
+        return 0.0;
+    return 2.0 * (double)nnz / (ms * 1e6);
 }
 
 #ifdef __cplusplus
 }
 #endif
-
 #endif /* SPMV_B200_UTILS_H */

@@ -1,7 +1,7 @@
-/* vector.h -- dense FP64 vector used for x and y.
+/* vector.h -- the dense FP64 vector that carries x and y.
  *
- * Same layout and entry points as the reference's include/vector.h:6-18
- * ({size_t len; double *data}); storage is 64-byte aligned and zero filled.
+ * ABI: { size_t len; double *data; } exactly as the reference's `vec`
+ * (include/vector.h:6-9).  Storage is 64-byte aligned.
  */
 #ifndef SPMV_B200_VECTOR_H
 #define SPMV_B200_VECTOR_H
@@ -13,23 +13,18 @@ extern "C" {
 #endif
 
 typedef struct {
-      size_t len;
-      double *data;
+    size_t len;
+    double *data;
 } vec;
 
-/* Allocate n zeroed doubles (64-B aligned). data == NULL on failure. */
-vec vec_create(size_t n);
-/* Release the storage; safe on NULL / already released vectors. */
-void vec_put(vec *v);
-/* Set every element to `value`. */
-void vec_fill(vec *v, double value);
-/* x[i] = rand() / RAND_MAX with the C library generator, never seeded here:
- * the sequence is therefore identical to the reference's (src/vector.c:36-41)
- * when both run in a fresh process. */
-void vec_fill_random(vec *v);
+vec vec_create(size_t count);            /* zero-filled; .data == NULL when out of memory     */
+void vec_put(vec *self);                 /* releases the storage; NULL and double put are fine */
+void vec_fill(vec *self, double value);  /* every element = value                              */
+void vec_fill_random(vec *self);         /* element i = rand() / RAND_MAX, C library generator,
+                                            never seeded here: a fresh process gets the same
+                                            x as the reference binary (src/vector.c:36-41)     */
 
 #ifdef __cplusplus
 }
 #endif
-
 #endif /* SPMV_B200_VECTOR_H */

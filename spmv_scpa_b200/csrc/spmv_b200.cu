@@ -1322,6 +1322,12 @@ extern "C" int spmv_b200_set_knob(const char *key, int value) {
             g_knobs.force_wide = value;
       else if (!strcmp(key, "adaptive_direct"))
             g_knobs.adaptive_direct = value;
+      else if (!strcmp(key, "l2_fetch_granularity")) {
+            // device-wide hint: bytes fetched from HBM on an L2 miss (32, 64 or 128)
+            if (ensure_device())
+                  return -ENODEV;
+            B200_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value));
+      }
       else
             return fail(-EINVAL, "unknown knob %s", key);
       return 0;
