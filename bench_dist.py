@@ -127,9 +127,16 @@ def run(args):
             graph_err = repr(e)[:200]
             it.graph = None
     reset()
+    sampler = None
+    if rank == 0:
+        from bench import ClockSampler  # bench.py is on sys.path
+        sampler = ClockSampler(local)
+        sampler.start()
+        time.sleep(0.25)
     torch.cuda.synchronize()
     dist.barrier()
     torch.cuda.synchronize()
+    t_region0 = time.time()
     c_before = sp.counters()["launches"]
     # The W warm-up steps run on the same stream immediately before the K timed steps, with
     # no host synchronisation in between: the ranks leave the host barrier up to a few ms
@@ -151,6 +158,7 @@ def run(args):
     end.record()
     torch.cuda.synchronize()
     dist.barrier()
+    clocks = sampler.stop(t_region0, time.time()) if sampler else None
     ms = torch.tensor([start.elapsed_time(end)], dtype=torch.float64, device=device)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
@@ -250,7 +258,7 @@ def run(args):
     dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
 
     if rank == 0:
-        from bench import measured_peak, ClockSampler  # noqa: F401  (bench.py is on sys.path)
+        from bench import measured_peak  # bench.py is on sys.path
         peak, peak_src = measured_peak()
         ms_step = total_ms / args.steps
         line = {
@@ -276,7 +284,7 @@ def run(args):
             "e2e": {"value": 2.0 * nnz_total / (float(e2e_dt.item()) * 1e9), "unit": "GFLOP/s",
                     "h2d_bytes_per_step": 8 * shard.M * world, "d2h_bytes_per_step": 8 * shard.M * world},
             "gpu_launches": launches,
-            "clocks": None,
+            "clocks": clocks,
             "parity": {"step1_vs_oracle": True, "worst_ratio_rank0": worst},
         }
         print(json.dumps(line))

@@ -1,0 +1,51 @@
+"""bench.py prints ONE JSON line with the keys the driver reads (reference arm on CPU here,
+the B200 arm under -m gpu)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+             "scaling", "vs_baseline", "dtype", "data", "config", "e2e", "cpu_baseline"}
+
+
+def run_bench(*args):
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], capture_output=True,
+                       text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    return json.loads(lines[0])
+
+
+def test_reference_arm_line():
+    d = run_bench("--impl", "reference", "--workload", "tiny", "--steps", "3", "--warmup", "1")
+    assert BASE_KEYS <= set(d)
+    assert d["impl"] == "reference" and d["unit"] == "GFLOP/s" and d["dtype"] == "f64"
+    assert d["vs_baseline"] is None and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["gpu_launches"] == 0
+    assert d["e2e"] == {"value": d["value"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"]
+    assert "workload" in d["config"] and "model" not in d["config"]
+
+
+@pytest.mark.gpu
+def test_b200_arm_line():
+    d = run_bench("--workload", "tiny", "--steps", "5", "--warmup", "3")
+    assert BASE_KEYS | {"roofline", "gpu_launches", "clocks"} <= set(d)
+    assert d["n_gpus"] == 1 and d["steps"] == 5 and d["value"] > 0
+    rf = d["roofline"]
+    assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and rf["peak"] > 1000
+    assert abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
+    assert d["gpu_launches"] >= d["steps"]
+    e = d["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] == 8 * d["config"]["cols"] and e["d2h_bytes_per_step"] == 8 * d["config"]["rows"]
+    assert e["value"] < d["value"]            # the host round trip cannot be free
+    assert d["cpu_baseline"]["value"] > 0
+    assert d["config"]["parity"]["csr"]["ok"] and d["config"]["parity"]["hll"]["ok"]
+    assert "sm_mhz" in d["clocks"] and isinstance(d["clocks"]["reasons"], list)
