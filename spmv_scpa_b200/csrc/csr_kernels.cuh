@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(1024)
       // Batches of U entries per lane: all index/value loads of a batch are
       // issued before the first gather, all gathers before the first FMA, so
       // U independent memory round trips overlap instead of chaining.
-      constexpr int U = 4;
+      constexpr int U = LPR == 32 ? 8 : 4; // a whole warp on a long row: deeper batches
       double acc0 = 0.0, acc1 = 0.0;
       for (OffT k = s + sub; k < e; k += LPR * U) {
             double a[U], xv[U];

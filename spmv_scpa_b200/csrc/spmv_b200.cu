@@ -39,7 +39,7 @@ struct Counters {
 struct Knobs {
       int stream_hints = 1; // matrix streams: L1 no_allocate + L2 evict_first
       int csr_stream_cfg = -1; // -1: pick from warps_per_block
-      int hll_vec = 1;         // vector width of the HLL headline kernel (1 measured best on B200)
+      int hll_vec = -1;        // vector width of the HLL headline kernel; -1 = by size of x
       int hll_stream_cfg = -1;
       int regular_lpr = -1; // force lanes-per-row (log2) of the adaptive base launch
       int force_wide = 0;   // use 64-bit row offsets even when NZ < 2^31 (tests)
@@ -983,17 +983,24 @@ int hll_run(spmv_b200_hll *h, int kernel, int wpb, const double *d_x, double *d_
             hll_warp_kernel<1, false><<<grid, threads, 0, st>>>(h->d_hoff, h->d_ja, h->d_as,
                                                                 h->n_hacks, h->M, d_x, d_y, push);
             break;
-      case SPMV_B200_HLL_WARP_HACK:
-            if (g_knobs.hll_vec == 1)
+      case SPMV_B200_HLL_WARP_HACK: {
+            // Measured (profiles/r1_kbench_c2_sweep.txt, r1_kbench_c3.txt): lane = row with
+            // 64/32-bit loads wins whenever x is cache friendly (C2: 99 % vs 97 % / 88 %); the
+            // 256/128-bit variant wins when x cannot live in L2 (C3, x = 128 MB: 3.8-4.6 ms vs 4.7)
+            int vec = g_knobs.hll_vec;
+            if (vec != 1 && vec != 2 && vec != 4)
+                  vec = h->N * 8 > (96ll << 20) ? 4 : 1;
+            if (vec == 1)
                   hll_warp_kernel<1, true><<<grid, threads, 0, st>>>(
                       h->d_hoff, h->d_ja, h->d_as, h->n_hacks, h->M, d_x, d_y, push);
-            else if (g_knobs.hll_vec == 2)
+            else if (vec == 2)
                   hll_warp_kernel<2, true><<<grid, threads, 0, st>>>(
                       h->d_hoff, h->d_ja, h->d_as, h->n_hacks, h->M, d_x, d_y, push);
             else
                   hll_warp_kernel<4, true><<<grid, threads, 0, st>>>(
                       h->d_hoff, h->d_ja, h->d_as, h->n_hacks, h->M, d_x, d_y, push);
             break;
+      }
       case SPMV_B200_HLL_STREAM: {
             const int cfg = hll_stream_cfg_for(wpb);
             auto &t = h->stream[cfg];

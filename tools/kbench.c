@@ -213,10 +213,12 @@ int main(int argc, char **argv) {
                         fprintf(stderr, "kbench: %s\n", spmv_b200_last_error());
                         return 1;
                   }
+                  spmv_b200_set_knob("hll_vec", 1);
                   run_hll(&c, hh, 2, 4, "vec=1");
                   spmv_b200_set_knob("hll_vec", 4);
                   run_hll(&c, hh, 2, 4, "vec=4");
-                  spmv_b200_set_knob("hll_vec", 1);
+                  spmv_b200_set_knob("hll_vec", -1);
+                  run_hll(&c, hh, 2, 16, "auto");
                   run_hll(&c, hh, 3, 8, "auto");
                   spmv_b200_hll_destroy(hh);
             }
@@ -297,7 +299,7 @@ int main(int argc, char **argv) {
                   for (int w = 0; w < 4; ++w)
                         run_hll(&c, hh, 2, wpbs[w], knob);
             }
-            spmv_b200_set_knob("hll_vec", 4);
+            spmv_b200_set_knob("hll_vec", -1);
             for (int cfg = 0; cfg < 6; ++cfg) {
                   spmv_b200_set_knob("hll_stream_cfg", cfg);
                   snprintf(knob, sizeof knob, "cfg=%d", cfg);
