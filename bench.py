@@ -175,8 +175,20 @@ def run_reference_arm(args):
         return 0
     import spmv_scpa_b200 as sp  # host generators only; no GPU work on this arm
     from oracle import oracle as O
-    desc, make = WORKLOADS[args.workload]
-    A = make(sp)
+    # same config as the B200 arm at this N (see run_single / bench_dist): c2 at N=1, the
+    # 128 x 128 x 128N stencil for N>1; for the 512^3 case a bounded sample (its first 64 planes,
+    # 451 M entries: the whole matrix does not fit int32-indexed host CSR)
+    sample = None
+    if args.workload == "c5":
+        desc = "3D 27-point stencil 512^3"
+        A = sp.gen_stencil27_rows(512, 512, 512, 0, 64 * 512 * 512)
+        sample = "rows of the first 64 of 512 planes (451 M of 3 610 M entries)"
+    elif args.gpus > 1 and args.workload == "c2":
+        desc = f"3D 27-point stencil 128x128x{128 * args.gpus} (one 128^3 slab per GPU in the B200 arm)"
+        A = sp.gen_stencil27(128, 128, 128 * args.gpus)
+    else:
+        desc, make = WORKLOADS[args.workload]
+        A = make(sp)
     x = np.random.default_rng(0).uniform(0, 1, A.N)
     arrays = (A.M, A.N, A.IRP, A.JA, A.AS)
     t0 = time.time()
@@ -191,7 +203,7 @@ def run_reference_arm(args):
         "config": {"workload": f"{args.workload}: {desc}", "format": "csr", "rows": A.M, "nnz": A.NZ,
                    "variant": best, "B_min_bytes": bmin},
         "cpu_baseline": {"value": v["gflops"], "unit": "GFLOP/s", "cores": v["cores"], "kind": kind,
-                         "sample": f"full {args.workload} matrix, {args.steps} SpMV passes per variant, median",
+                         "sample": (sample or f"full matrix ({desc})") + f", {args.steps} SpMV passes per variant, median",
                          "variants": variants, "host_threads": nthreads, "build": O.ref_kind() if kind == "reference" else "port"},
         "e2e": {"value": v["gflops"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.time() - t0,
