@@ -212,3 +212,70 @@ def test_large_file_errors_keep_reference_order(sp, O, tmp_path):
         with pytest.raises(OSError) as ei:
             loader(q2)
         assert ei.value.errno == errno.EIO
+
+
+# ------------------------------------------------------------- property-based cases --
+from hypothesis import given, settings, strategies as st, HealthCheck  # noqa: E402
+
+
+@st.composite
+def mtx_files(draw):
+    field = draw(st.sampled_from(["real", "pattern"]))
+    sym = draw(st.sampled_from(["general", "symmetric", "skew-symmetric"]))
+    M = draw(st.integers(1, 70))
+    N = M if sym != "general" else draw(st.integers(1, 70))
+    nnz = draw(st.integers(0, 120))
+    ent = []
+    for _ in range(nnz):
+        i, j = draw(st.integers(1, M)), draw(st.integers(1, N))
+        if sym != "general" and j > i:
+            i, j = j, i
+        v = draw(st.floats(allow_nan=False, allow_infinity=False, width=64))
+        ent.append((i, j, v))
+    sep = draw(st.sampled_from([" ", "\t", "  ", " \t "]))
+    comments = draw(st.lists(st.sampled_from(["% a comment", "%", "%% odd"]), max_size=3))
+    blank = draw(st.booleans())
+    case = draw(st.sampled_from([str.lower, str.upper, str.title]))
+    lines = [f"%%MatrixMarket {case('matrix')} {case('coordinate')} {case(field)} {case(sym)}"] + comments
+    if blank:
+        lines.append("")
+    lines.append(f"{M}{sep}{N}{sep}{nnz}")
+    for i, j, v in ent:
+        lines.append(f"{i}{sep}{j}" + ("" if field == "pattern" else f"{sep}{v!r}"))
+    return "\n".join(lines) + "\n"
+
+
+@settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(text=mtx_files())
+def test_loader_and_packer_properties(sp, O, tmp_path, text):
+    """Any well-formed coordinate file: product loader == oracle port (== reference when built),
+    and unpacking either HLL layout gives back the CSR rows exactly."""
+    p = tmp_path / "h.mtx"
+    p.write_text(text)
+    want = O.load_mtx(str(p))
+    if O.ref_available():
+        ref = O.ref_load_mtx(str(p))
+        assert np.array_equal(ref[2], want[2]) and np.array_equal(ref[3], want[3])
+        assert np.array_equal(bits(ref[4]), bits(want[4]))
+    A = sp.io_load_csr(str(p))
+    assert (A.M, A.N) == (want[0], want[1])
+    assert np.array_equal(A.IRP, want[2]) and np.array_equal(A.JA, want[3])
+    assert np.array_equal(bits(A.AS), bits(want[4]))
+    for cm in (False, True):
+        H = sp.csr_to_hll(A, cm)
+        for b in range(H.num_blocks):
+            m, n, nzb, w, ja, as_ = H.block(b)
+            assert n == A.N and m == min(32, A.M - 32 * b)
+            got = 0
+            for i in range(m):
+                r = 32 * b + i
+                k0, k1 = A.IRP[r], A.IRP[r + 1]
+                idx = [(j * m + i) if cm else (i * w + j) for j in range(w)]
+                row_ja, row_as = ja[idx], as_[idx]
+                ln = k1 - k0
+                assert np.array_equal(row_ja[:ln], A.JA[k0:k1])
+                assert np.array_equal(bits(row_as[:ln]), bits(A.AS[k0:k1]))
+                assert (row_ja[ln:] == -1).all() and (row_as[ln:] == 0.0).all()
+                got += ln
+            assert got == nzb
+            assert w == max([A.IRP[32 * b + i + 1] - A.IRP[32 * b + i] for i in range(m)] + [0])
