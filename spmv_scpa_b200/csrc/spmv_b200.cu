@@ -432,8 +432,12 @@ void run_adaptive(const CsrArgs &a, const Segment &sg) {
       X(23, 512, 1, 2, 8192, 2, true, true)                                                        \
       X(24, 256, 1, 2, 4096, 8, true, true)                                                        \
       X(25, 512, 1, 3, 4096, 2, true, true)                                                        \
-      X(26, 512, 1, 4, 2048, 2, true, true)
-constexpr int kNumStreamCfg = 27;
+      X(26, 512, 1, 4, 2048, 2, true, true)                                                        \
+      X(27, 512, 1, 6, 2048, 2, true, true)                                                        \
+      X(28, 256, 1, 4, 2048, 4, true, true)                                                        \
+      X(29, 512, 1, 4, 1024, 2, true, true)                                                        \
+      X(30, 512, 1, 8, 1024, 2, true, true)
+constexpr int kNumStreamCfg = 31;
 
 struct StreamShape {
       int threads, lpr, stages, cap, passes;
@@ -491,7 +495,9 @@ int stream_cfg_for(int wpb, double mean_len, bool regular) {
             return wpb <= 4 ? 22 : 25;
       if (mean_len >= 12.0)
             return wpb <= 2 ? 10 : (wpb <= 4 ? 12 : 13);
-      return wpb <= 2 ? 17 : (wpb <= 4 ? 18 : 19);
+      // short rows (5-point stencils ...): the entry-split tiles win here too -- 70 % vs 59 % of
+      // peak on a 3000^2 Poisson matrix (profiles/r1_kbench_poisson3000.txt)
+      return wpb <= 2 ? 24 : 26;
 }
 
 template <typename OffT>

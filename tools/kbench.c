@@ -23,7 +23,7 @@
 #include "spmv_b200.h"
 #include "spmv_gen.h"
 
-static int g_reps = 20, g_warmup = 3, g_flush = 0, g_quick = 0, g_profile = 0;
+static int g_reps = 20, g_warmup = 3, g_flush = 0, g_quick = 0, g_profile = 0, g_cfg_from = -1;
 static double g_peak = 6559.7; /* MEASURED_PEAKS.json hbm_gbs of this pool */
 static const char *g_only = "";
 
@@ -142,6 +142,8 @@ int main(int argc, char **argv) {
                   g_flush = 1;
             else if (!strcmp(argv[i], "--quick"))
                   g_quick = 1;
+            else if (!strcmp(argv[i], "--cfg-from") && i + 1 < argc)
+                  g_cfg_from = atoi(argv[++i]);
             else if (!strcmp(argv[i], "--knob") && i + 1 < argc) {
                   char key[64];
                   int val = 0;
@@ -256,7 +258,7 @@ int main(int argc, char **argv) {
             spmv_b200_set_knob("adaptive_direct", 0);
             for (int w = 0; w < 3; ++w)
                   run_csr(&c, h, 4, wpbs[w], "auto");
-            for (int cfg = g_quick ? 10 : 0; cfg < 27; ++cfg) {
+            for (int cfg = g_cfg_from >= 0 ? g_cfg_from : (g_quick ? 10 : 0); cfg < 31; ++cfg) {
                   spmv_b200_set_knob("csr_stream_cfg", cfg);
                   snprintf(knob, sizeof knob, "cfg=%d", cfg);
                   run_csr(&c, h, 4, 4, knob);
