@@ -170,3 +170,35 @@ def test_c2_full_size_parity(sp, O, torch, c2):
     assert ok
     h.close()
     hh.close()
+
+
+def test_shard_with_column_offset_from_host_arrays(sp, O, torch):
+    """A row slab uploaded with col_offset (how a rank holds its part of A): indices are stored
+    relative to the local x slice [c0, c1), the result equals the same rows of the full product."""
+    nx, ny, nz = 10, 9, 12
+    plane = nx * ny
+    full = sp.gen_stencil27(nx, ny, nz)
+    x = np.random.default_rng(4).uniform(-1, 1, full.N)
+    y_full = O.csr_spmv(full.M, full.IRP, full.JA, full.AS, x)
+    bound = O.csr_abs_bound(full.M, full.IRP, full.JA, full.AS, x)
+    z0, z1 = 4, 9
+    r0, r1 = z0 * plane, z1 * plane
+    c0, c1 = (z0 - 1) * plane, (z1 + 1) * plane
+    part = sp.gen_stencil27_rows(nx, ny, nz, r0, r1)          # global column indices
+    for wide in (0, 1):
+        sp.set_knob("force_wide", wide)
+        try:
+            h = sp.CsrDevice.from_arrays(part.M, c1 - c0, part.IRP, part.JA, part.AS, col_offset=c0,
+                                         cuts=[plane, part.M - plane])
+        finally:
+            sp.set_knob("force_wide", 0)
+        _, ja_dev, _ = h.download()
+        assert np.array_equal(ja_dev, part.JA - c0)
+        xl = dev(torch, x[c0:c1])
+        y = torch.full((part.M,), float("nan"), dtype=torch.float64, device="cuda")
+        for kernel in (2, 4, 0, 1, 3):
+            y.fill_(float("nan"))
+            h.spmv(xl, y, kernel=kernel)
+            ok, worst = O.check_tolerance(y.cpu().numpy(), y_full[r0:r1], bound[r0:r1], TOL)
+            assert ok, (wide, kernel, worst)
+        h.close()
