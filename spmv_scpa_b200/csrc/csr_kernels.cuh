@@ -24,11 +24,6 @@
 
 namespace b200 {
 
-struct Tuning {
-      int stream_hints; // 1: no_allocate + evict_first on matrix streams
-      int x_evict_last; // 1: evict_last policy on x gathers
-};
-
 // ------------------------------------------------------------------------
 // LPR lanes per row.  `rowlist` == nullptr: rows [row0, row0+nrows) in order;
 // otherwise rows rowlist[0..nrows).  Rows longer than `max_len` are skipped
