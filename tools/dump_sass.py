@@ -8,8 +8,9 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rnd = sys.argv[1] if len(sys.argv) > 1 else "r1"
-WANT = [r"csr_stream_kernelILi512ELi4ELi2ELi4096ELi1ELb1EiE", r"hll_warp_kernelILi1ELb1EE",
-        r"csr_vec_kernelILi8EiLb1EE", r"hll_stream_kernelILi8ELi2ELi8192EE"]
+WANT = [r"csr_stream_kernelILi512ELi4ELi2ELi4096ELi1ELb1ELb0EiE",   # C2 headline: row-wise staged tiles
+        r"csr_stream_kernelILi512ELi1ELi4ELi2048ELi2ELb1ELb1EiE",   # entry-split staged tiles
+        r"hll_warp_kernelILi1ELb1EE", r"csr_vec_kernelILi8EiLb1EE", r"hll_stream_kernelILi8ELi2ELi8192EE"]
 txt = subprocess.run(["cuobjdump", "-sass", os.path.join(ROOT, "spmv_scpa_b200/lib/libspmv_b200.so")],
                      capture_output=True, text=True).stdout
 parts = re.split(r"(?=\t\tFunction : )", txt)
