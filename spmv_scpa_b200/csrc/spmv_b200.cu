@@ -436,8 +436,12 @@ void run_adaptive(const CsrArgs &a, const Segment &sg) {
       X(27, 512, 1, 6, 2048, 2, true, true)                                                        \
       X(28, 256, 1, 4, 2048, 4, true, true)                                                        \
       X(29, 512, 1, 4, 1024, 2, true, true)                                                        \
-      X(30, 512, 1, 8, 1024, 2, true, true)
-constexpr int kNumStreamCfg = 31;
+      X(30, 512, 1, 8, 1024, 2, true, true)                                                        \
+      X(31, 128, 1, 2, 1024, 8, true, true)                                                        \
+      X(32, 128, 1, 3, 1024, 8, true, true)                                                        \
+      X(33, 256, 1, 2, 2048, 4, true, true)                                                        \
+      X(34, 256, 1, 2, 1024, 4, true, true)
+constexpr int kNumStreamCfg = 35;
 
 struct StreamShape {
       int threads, lpr, stages, cap, passes;
@@ -491,8 +495,9 @@ int launch_stream_cfg(int cfg, const CsrArgs &a, const StreamPlan &sp) {
 int stream_cfg_for(int wpb, double mean_len, bool regular) {
       if (g_knobs.csr_stream_cfg >= 0 && g_knobs.csr_stream_cfg < kNumStreamCfg)
             return g_knobs.csr_stream_cfg;
-      if (!regular) // power-law / ragged: split tiles by entry, not by row
-            return wpb <= 4 ? 22 : 25;
+      if (!regular) // power-law / ragged: split tiles by entry, not by row (cfg 33: 30 % vs 26 %
+                    // for cfg 22 on R-MAT 22, profiles/r1_kbench_rmat22_split_cfgs2.txt)
+            return wpb <= 4 ? 33 : 25;
       if (mean_len >= 12.0)
             return wpb <= 2 ? 10 : (wpb <= 4 ? 12 : 13);
       // short rows (5-point stencils ...): the entry-split tiles win here too -- 70 % vs 59 % of

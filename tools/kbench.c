@@ -258,7 +258,7 @@ int main(int argc, char **argv) {
             spmv_b200_set_knob("adaptive_direct", 0);
             for (int w = 0; w < 3; ++w)
                   run_csr(&c, h, 4, wpbs[w], "auto");
-            for (int cfg = g_cfg_from >= 0 ? g_cfg_from : (g_quick ? 10 : 0); cfg < 31; ++cfg) {
+            for (int cfg = g_cfg_from >= 0 ? g_cfg_from : (g_quick ? 10 : 0); cfg < 35; ++cfg) {
                   spmv_b200_set_knob("csr_stream_cfg", cfg);
                   snprintf(knob, sizeof knob, "cfg=%d", cfg);
                   run_csr(&c, h, 4, 4, knob);
