@@ -173,14 +173,17 @@ void spmv_b200_hll_destroy(spmv_b200_hll *h);
 void spmv_b200_release_all(void);
 /* Timing policy of the reference-style entry points (defaults 1 / 3; also
  * settable with SPMV_B200_WARMUP / SPMV_B200_REPS).  The returned duration is
- * the median of the timed repetitions. */
+ * the median of the timed repetitions.  reps = 0 asks for no separately timed
+ * launches: the pipelined entry (banded matrix, page-locked x and y: x is
+ * uploaded in column order while row chunks compute and y chunks travel back)
+ * then returns the span of its single pass; other paths time one launch. */
 void spmv_b200_set_timing(int warmup, int reps);
 /* Counters since load: kernel launches issued, bytes copied H2D / D2H. */
 void spmv_b200_counters(int64_t *launches, int64_t *h2d_bytes,
                         int64_t *d2h_bytes);
 
 /* Experiment knobs used by bin/kbench sweeps ("stream_hints", "csr_stream_cfg",
- * "hll_vec", "hll_stream_cfg", "regular_lpr", "adaptive_direct", "force_wide").  0 or -EINVAL.  Knobs that
+ * "hll_vec", "hll_stream_cfg", "regular_lpr", "adaptive_direct", "force_wide", "pipeline").  0 or -EINVAL.  Knobs that
  * change planning ("regular_lpr") must be set before a handle is created. */
 int spmv_b200_set_knob(const char *key, int value);
 

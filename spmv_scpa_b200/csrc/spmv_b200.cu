@@ -44,6 +44,7 @@ struct Knobs {
       int regular_lpr = -1; // force lanes-per-row (log2) of the adaptive base launch
       int force_wide = 0;   // use 64-bit row offsets even when NZ < 2^31 (tests)
       int adaptive_direct = 0; // 1: the adaptive path never uses the TMA-staged kernel
+      int pipeline = 1;        // host-buffer pipeline in the reference-style CSR entry points
       int warmup = 1, reps = 3;
 } g_knobs;
 
@@ -173,6 +174,11 @@ struct spmv_b200_csr {
       std::vector<long long> h_irp; // host copy of the row offsets (planning)
       std::vector<Segment> segs;
       int device = 0;
+      // host-buffer pipeline of the reference-style entry points (banded matrices): row chunks
+      // with their own launch plans, and how much of x each chunk needs to have arrived
+      std::vector<Segment> pipe_segs;
+      std::vector<long long> pipe_x_hi; // x[0, pipe_x_hi[c]) must be on the device before chunk c
+      int pipe_state = 0;               // 0 not tried, 1 usable, -1 not worth it
 };
 
 namespace {
@@ -548,12 +554,18 @@ int run_kernel(spmv_b200_csr *h, int kernel, int wpb, Segment &sg, const CsrArgs
       }
 }
 
+int csr_run_segment(spmv_b200_csr *h, Segment &sg, int kernel, int wpb, const double *d_x,
+                    double *d_y, const PushArgs &push, cudaStream_t st) {
+      CsrArgs a{h, d_x, d_y, push, st, 32 * wpb};
+      return h->wide ? run_kernel<long long>(h, kernel, wpb, sg, a)
+                     : run_kernel<int>(h, kernel, wpb, sg, a);
+}
+
 int csr_run(spmv_b200_csr *h, int kernel, int wpb, long long row0, long long row1,
             const double *d_x, double *d_y, const PushArgs &push, void *stream) {
       if (!h)
             return fail(-EINVAL, "null CSR handle");
       wpb = clamp_wpb(wpb);
-      CsrArgs a{h, d_x, d_y, push, as_stream(stream), 32 * wpb};
       bool any = false;
       for (auto &sg : h->segs) {
             if (sg.r0 < row0 || sg.r1 > row1)
@@ -561,8 +573,7 @@ int csr_run(spmv_b200_csr *h, int kernel, int wpb, long long row0, long long row
             if (sg.r1 == sg.r0)
                   continue;
             any = true;
-            int rc = h->wide ? run_kernel<long long>(h, kernel, wpb, sg, a)
-                             : run_kernel<int>(h, kernel, wpb, sg, a);
+            int rc = csr_run_segment(h, sg, kernel, wpb, d_x, d_y, push, as_stream(stream));
             if (rc)
                   return rc;
       }
@@ -573,6 +584,48 @@ int csr_run(spmv_b200_csr *h, int kernel, int wpb, long long row0, long long row
       if (e != cudaSuccess)
             return fail(-EIO, "CSR kernel %d launch failed: %s", kernel, cudaGetErrorString(e));
       return 0;
+}
+
+// Row chunks for the host-buffer pipeline.  Usable when the matrix is banded enough that the
+// first half of the rows needs at most ~3/4 of x: then x can be uploaded in column order while
+// earlier chunks already compute and earlier parts of y already travel back.
+constexpr int kPipeChunks = 8;
+
+void build_pipe(spmv_b200_csr *h, const int *host_ja) {
+      h->pipe_state = -1;
+      if (!host_ja || h->col_offset != 0 || h->M < kPipeChunks * 4096 || h->NZ < (1 << 22))
+            return;
+      std::vector<long long> cut(kPipeChunks + 1, 0);
+      for (int c = 1; c < kPipeChunks; ++c) {
+            const long long want = h->NZ / kPipeChunks * c;
+            long long r = std::lower_bound(h->h_irp.begin(), h->h_irp.end(), want) - h->h_irp.begin();
+            r = std::min(h->M, (r + 31) / 32 * 32);
+            cut[c] = std::max(r, cut[c - 1]);
+      }
+      cut[kPipeChunks] = h->M;
+      std::vector<long long> hi(kPipeChunks, 0);
+      long long running = 0;
+      for (int c = 0; c < kPipeChunks; ++c) {
+            const long long k0 = h->h_irp[cut[c]], k1 = h->h_irp[cut[c + 1]];
+            int mx = -1;
+#pragma omp parallel for reduction(max : mx) schedule(static)
+            for (long long k = k0; k < k1; ++k)
+                  mx = host_ja[k] > mx ? host_ja[k] : mx;
+            running = std::max(running, (long long)mx + 1);
+            hi[c] = running;
+      }
+      hi[kPipeChunks - 1] = h->N; // whatever is left of x goes up with the last block
+      if (hi[kPipeChunks / 2 - 1] * 4 > h->N * 3)
+            return; // not banded: the first half of the rows already needs (almost) all of x
+      for (int c = 0; c < kPipeChunks; ++c) {
+            Segment sg;
+            sg.r0 = cut[c], sg.r1 = cut[c + 1];
+            if (build_adaptive(h, sg))
+                  return;
+            h->pipe_segs.push_back(sg);
+      }
+      h->pipe_x_hi = hi;
+      h->pipe_state = 1;
 }
 
 } // namespace
@@ -734,7 +787,9 @@ extern "C" spmv_b200_csr *spmv_b200_csr_gen_stencil27(int nx, int ny, int nz, in
 extern "C" void spmv_b200_csr_destroy(spmv_b200_csr *h) {
       if (!h)
             return;
-      for (auto &sg : h->segs) {
+      std::vector<Segment> *groups[2] = {&h->segs, &h->pipe_segs};
+      for (auto *grp : groups)
+      for (auto &sg : *grp) {
             for (auto &l : sg.lists)
                   free_list(l);
             free_split(sg.split);
@@ -1310,7 +1365,7 @@ extern "C" int spmv_b200_flush_l2(void *stream) {
 
 extern "C" void spmv_b200_set_timing(int warmup, int reps) {
       g_knobs.warmup = std::max(0, warmup);
-      g_knobs.reps = std::max(1, reps);
+      g_knobs.reps = std::max(0, reps); // 0: no separately timed launches (pipelined entry only)
 }
 
 extern "C" void spmv_b200_counters(int64_t *launches, int64_t *h2d_bytes, int64_t *d2h_bytes) {
@@ -1340,6 +1395,8 @@ extern "C" int spmv_b200_set_knob(const char *key, int value) {
             g_knobs.force_wide = value;
       else if (!strcmp(key, "adaptive_direct"))
             g_knobs.adaptive_direct = value;
+      else if (!strcmp(key, "pipeline"))
+            g_knobs.pipeline = value;
       else if (!strcmp(key, "l2_fetch_granularity")) {
             // device-wide hint: bytes fetched from HBM on an L2 miss (32, 64 or 128)
             if (ensure_device())
@@ -1621,7 +1678,7 @@ double entry_common(long long M, long long N, const double *x, double *y, Run &&
             return -1.0;
       }
       g_counters.h2d += N * 8;
-      std::vector<double> ms((size_t)g_knobs.reps);
+      std::vector<double> ms((size_t)std::max(1, g_knobs.reps));
       if (timed(ms.data()))
             return -1.0;
       if (M && cudaMemcpy(y, g_dy, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost) !=
@@ -1635,6 +1692,80 @@ double entry_common(long long M, long long N, const double *x, double *y, Run &&
       return med > 0.0 ? med : 1e-6;
 }
 
+// Is this host pointer page-locked (cudaHostAlloc / cudaHostRegister)?  Only then do async
+// copies overlap with kernels and with each other.
+bool is_pinned(const void *p) {
+      cudaPointerAttributes at{};
+      if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+      }
+      return at.type == cudaMemoryTypeHost;
+}
+
+// Host-buffer pipeline for banded matrices (pinned x and y): x goes up in column order on one
+// stream, row chunk c starts as soon as the columns it references have arrived, and its slice
+// of y travels back on a third stream while later chunks compute -- PCIe is used in both
+// directions at once instead of x-up, compute, y-down in sequence.  Returns the time from the
+// first chunk's start to the last chunk's end on the compute stream (ms), or <= 0 on error.
+double csr_pipeline_pass(spmv_b200_csr *h, int kernel, int wpb, const double *x, double *y) {
+      static cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
+      static cudaEvent_t ev_in[kPipeChunks], ev_k[kPipeChunks], t0, t1;
+      if (!s_in) {
+            if (cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking) != cudaSuccess ||
+                cudaStreamCreateWithFlags(&s_cmp, cudaStreamNonBlocking) != cudaSuccess ||
+                cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking) != cudaSuccess) {
+                  fail(-EIO, "pipeline streams: %s", cudaGetErrorString(cudaGetLastError()));
+                  s_in = nullptr;
+                  return -1.0;
+            }
+            for (int c = 0; c < kPipeChunks; ++c) {
+                  cudaEventCreateWithFlags(&ev_in[c], cudaEventDisableTiming);
+                  cudaEventCreateWithFlags(&ev_k[c], cudaEventDisableTiming);
+            }
+            cudaEventCreate(&t0);
+            cudaEventCreate(&t1);
+      }
+      PushArgs none{};
+      long long lo = 0;
+      for (int c = 0; c < kPipeChunks; ++c) {
+            const long long hi = h->pipe_x_hi[c];
+            if (hi > lo)
+                  cudaMemcpyAsync(g_dx + lo, x + lo, (size_t)(hi - lo) * 8, cudaMemcpyHostToDevice,
+                                  s_in);
+            cudaEventRecord(ev_in[c], s_in);
+            lo = std::max(lo, hi);
+      }
+      int rc = 0;
+      for (int c = 0; c < kPipeChunks && !rc; ++c) {
+            Segment &sg = h->pipe_segs[c];
+            cudaStreamWaitEvent(s_cmp, ev_in[c], 0);
+            if (c == 0)
+                  cudaEventRecord(t0, s_cmp);
+            if (sg.r1 > sg.r0)
+                  rc = csr_run_segment(h, sg, kernel, wpb, g_dx, g_dy, none, s_cmp);
+            cudaEventRecord(ev_k[c], s_cmp);
+            cudaStreamWaitEvent(s_out, ev_k[c], 0);
+            if (sg.r1 > sg.r0)
+                  cudaMemcpyAsync(y + sg.r0, g_dy + sg.r0, (size_t)(sg.r1 - sg.r0) * 8,
+                                  cudaMemcpyDeviceToHost, s_out);
+      }
+      cudaEventRecord(t1, s_cmp);
+      cudaError_t e1 = cudaStreamSynchronize(s_cmp), e2 = cudaStreamSynchronize(s_out),
+                  e3 = cudaStreamSynchronize(s_in);
+      if (rc)
+            return -1.0;
+      if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+            fail(-EIO, "pipelined SpMV failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return -1.0;
+      }
+      g_counters.h2d += h->N * 8;
+      g_counters.d2h += h->M * 8;
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, t0, t1);
+      return ms > 0.f ? (double)ms : 1e-6;
+}
+
 double csr_entry(const sparse_csr *A, const double *x, double *y, int kernel) {
       if (!A) {
             fail(-EINVAL, "null sparse_csr");
@@ -1646,10 +1777,30 @@ double csr_entry(const sparse_csr *A, const double *x, double *y, int kernel) {
       spmv_b200_csr *h = cached_csr(A);
       if (!h)
             return -1.0;
-      const int wpb = t_csr_wpb;
+      const int wpb = clamp_wpb(t_csr_wpb);
+
+      // banded matrix + page-locked buffers + a kernel that can run on row chunks: pipeline
+      const bool chunkable = kernel == SPMV_B200_CSR_ADAPTIVE || kernel == SPMV_B200_CSR_STREAM;
+      if (g_knobs.pipeline && chunkable && x && y) {
+            if (h->pipe_state == 0)
+                  build_pipe(h, A->JA);
+            if (h->pipe_state == 1 && is_pinned(x) && is_pinned(y) &&
+                ensure_vectors((size_t)A->N, (size_t)A->M) == 0) {
+                  const double pass_ms = csr_pipeline_pass(h, kernel, wpb, x, y);
+                  if (pass_ms <= 0.0)
+                        return -1.0;
+                  if (g_knobs.reps <= 0)
+                        return pass_ms; // y is already home; no separately timed launches wanted
+                  std::vector<double> ms((size_t)g_knobs.reps);
+                  if (spmv_b200_csr_time(h, kernel, wpb, g_dx, g_dy, 0, g_knobs.reps, 0, ms.data(),
+                                         nullptr))
+                        return -1.0;
+                  return median_of(ms);
+            }
+      }
       return entry_common(A->M, A->N, x, y, [&](double *ms) {
-            return spmv_b200_csr_time(h, kernel, wpb, g_dx, g_dy, g_knobs.warmup, g_knobs.reps, 0,
-                                      ms, nullptr);
+            return spmv_b200_csr_time(h, kernel, wpb, g_dx, g_dy, g_knobs.warmup,
+                                      std::max(1, g_knobs.reps), 0, ms, nullptr);
       });
 }
 
@@ -1666,8 +1817,8 @@ double hll_entry(const sparse_hll *H, const double *x, double *y, int kernel, in
             return -1.0;
       const int wpb = t_hll_wpb;
       return entry_common(H->M, H->N, x, y, [&](double *ms) {
-            return spmv_b200_hll_time(h, kernel, wpb, g_dx, g_dy, g_knobs.warmup, g_knobs.reps, 0,
-                                      ms, nullptr);
+            return spmv_b200_hll_time(h, kernel, wpb, g_dx, g_dy, g_knobs.warmup,
+                                      std::max(1, g_knobs.reps), 0, ms, nullptr);
       });
 }
 

@@ -158,3 +158,45 @@ def test_timer_c_api(sp):
     assert 0.0 < ms < 1000.0
     L.timer_destroy(C.byref(t))
     L.spmv_b200_dfree(buf)
+
+
+def test_pipelined_entry_with_pinned_buffers(sp, O):
+    """Banded matrix + page-locked x / y: the CSR entry points upload x in column order, run row
+    chunks as their columns arrive and send y chunks back meanwhile.  Same results as the plain
+    path, for both chunkable kernels, with and without separately timed repetitions; a
+    non-banded matrix with pinned buffers must quietly take the plain path."""
+    import ctypes as C
+    L = sp._lib.b200
+
+    def pinned(n):
+        p = L.spmv_b200_host_alloc(max(n, 1) * 8)
+        assert p
+        return p, np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(n,))
+
+    for make, banded in ((lambda: sp.gen_stencil27(64, 64, 64), True),
+                         (lambda: sp.gen_uniform_random(300000, 16, 5), False)):
+        A = make()
+        px, xh = pinned(A.N)
+        py, yh = pinned(A.M)
+        xh[:] = np.random.default_rng(8).uniform(-1, 1, A.N)
+        IRP, JA, AS = A.IRP.copy(), A.JA.copy(), A.AS.copy()
+        y_ref = oracle_y(O, A.M, A.N, IRP, JA, AS, xh.copy())
+        bound = O.csr_abs_bound(A.M, IRP, JA, AS, xh.copy())
+        dp = C.POINTER(C.c_double)
+        for fn in (L.csr_spmv_cuda_halfwarp_row, L.csr_spmv_cuda_halfwarp_row_text, L.csr_spmv_cuda_warp_row):
+            for reps in (0, 2):
+                sp.set_timing(1, reps)
+                L.set_csr_warps_per_block(4)
+                yh[:] = np.nan
+                c0 = sp.counters()
+                ms = fn(A.ptr, C.cast(px, dp), C.cast(py, dp), None)
+                c1 = sp.counters()
+                assert ms > 0, sp._lib.last_error()
+                ok, worst = O.check_tolerance(yh, y_ref, bound, TOL)
+                assert ok, (banded, fn.__name__, reps, worst)
+                assert c1["h2d_bytes"] - c0["h2d_bytes"] >= 8 * A.N     # x went up (plus plans on first use)
+                assert c1["d2h_bytes"] - c0["d2h_bytes"] == 8 * A.M
+        sp.set_timing(1, 3)
+        sp.release_all()
+        L.spmv_b200_host_free(px)
+        L.spmv_b200_host_free(py)
