@@ -16,6 +16,9 @@
  *     spmv_b200_last_error() holds a message for the calling thread.
  *   - "d_" parameters are device pointers, everything else is host memory.
  *   - there is NO CPU fallback: with no usable GPU every create/run fails.
+ *   - threading: a handle is used by one thread at a time (launch plans are built lazily on
+ *     first use of a kernel); different handles may be used concurrently; the reference-style
+ *     entry points of cuda_csr.h / cuda_hll.h serialise on an internal lock.
  */
 #ifndef SPMV_B200_H
 #define SPMV_B200_H
