@@ -407,6 +407,33 @@ def ref_csr_omp(A: RefCsr, x, threads, schedule="guided"):
     return b.bench.duration_ms, _take(b.bench), b.num_threads
 
 
+def ref_hll_bench(A: RefCsr, x, threads):
+    """The reference's HLL CPU paths on its own row-major packing of A: serial
+    (src/hll.c:127-150 via bench_hll_serial) and OpenMP guided over hacks (:178-211 via
+    bench_hll_omp).  Returns (serial_ms, omp_ms, y_serial)."""
+    addr = ref().csr_to_hll(A.ptr, False)
+    if _is_err(addr):
+        raise MemoryError("reference csr_to_hll failed")
+    try:
+        H = C.cast(C.c_void_p(addr), C.POINTER(_hll))
+        xa = aligned_copy(x, np.float64)
+        b = _bench()
+        rc = ref().bench_hll_serial(H, _cd(xa), C.byref(b))
+        if rc:
+            raise OSError(-rc, "bench_hll_serial")
+        serial_ms, y = b.duration_ms, _take(b)
+        bo = _bench_omp()
+        bo.num_threads = threads
+        rc = ref().bench_hll_omp(H, _cd(xa), C.byref(bo))
+        if rc:
+            raise OSError(-rc, "bench_hll_omp")
+        omp_ms = bo.bench.duration_ms
+        _take(bo.bench)
+    finally:
+        ref().hll_free(addr)
+    return serial_ms, omp_ms, y
+
+
 def ref_rand_x(n):
     """x as the reference makes it: vec_fill_random -> rand()/RAND_MAX (src/vector.c:36-41)."""
     v = ref().vec_create(n)

@@ -180,3 +180,19 @@ def test_golden_rand_x_matches_reference(O, have_ref):
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, check=True).stdout
     got = np.frombuffer(bytes.fromhex(out.decode()), np.float64)
     assert np.array_equal(got, np.load(os.path.join(GOLDEN, "rand_x64.npy")))
+
+
+def test_reference_hll_cpu_paths_agree_with_its_csr(O, have_ref):
+    """The reference's serial HLL SpMV (src/hll.c:127-150) on its own packing equals its serial
+    CSR result on the golden inputs (both are the reference; this pins the HLL leg of the CPU
+    baseline that bench.py reports)."""
+    if not have_ref:
+        pytest.skip("oracle/_ref not built")
+    for case in ("rect_general", "tricky_sym", "long_row_mixedcase"):
+        g = golden(case)
+        A = O.RefCsr(int(g["M"]), int(g["N"]), g["IRP"], g["JA"], g["AS"])
+        ser_ms, omp_ms, y = O.ref_hll_bench(A, g["x"], 2)
+        bound = O.csr_abs_bound(int(g["M"]), g["IRP"], g["JA"], g["AS"], g["x"])
+        ok, worst = O.check_tolerance(y, g["y"], bound, TOL)
+        assert ok, (case, worst)
+        assert ser_ms >= 0 and omp_ms >= 0
