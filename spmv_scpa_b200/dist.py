@@ -118,6 +118,18 @@ class ExchangePlan:
     def halo_bytes(self):
         return 8 * sum(g1 - g0 for _, g0, g1 in self.recv)
 
+    def max_push_targets(self):
+        """Largest number of peers any single boundary segment has to feed.  The fused push
+        epilogue of the SpMV kernels carries two destinations; a plan that needs more (an
+        all-gather over more than three ranks) has to exchange through NCCL instead."""
+        worst = 0
+        for r0, r1, is_boundary in self.segments:
+            if not is_boundary:
+                continue
+            n = sum(1 for _, g0, g1 in self.send if max(g0 - self.r0, r0) < min(g1 - self.r0, r1))
+            worst = max(worst, n)
+        return worst
+
 
 def gather_table(dist, r0, r1, c0, c1, device="cpu"):
     """all-gather of the four integers that define every rank's shard."""
@@ -155,6 +167,9 @@ class DistSpMV:
         self.graph, self.graph_steps = None, 0
         self._peer_ptrs = None
         self._flag = None
+        if mode == "push" and plan.max_push_targets() > 2:
+            # e.g. a general matrix on 4+ ranks: every rank needs every slice
+            self.mode = mode = "nccl"
         if mode == "push":
             self._setup_push()
         self._initial_exchange()

@@ -51,10 +51,16 @@ def test_exchange_plan_shapes():
     p0 = D.ExchangePlan(0, table)
     assert p0.send == [(1, 300, 400)] and p0.recv == [(1, 400, 500)]
     assert p0.segments == [(300, 400, True), (0, 300, False)]
+    assert p1.max_push_targets() == 1 and p0.max_push_targets() == 1
     # all-gather case: everybody needs everything -> no interior
     full = [(0, 50, 0, 100), (50, 100, 0, 100)]
     q = D.ExchangePlan(0, full)
     assert q.segments == [(0, 50, True)] and q.cuts == []
+    assert q.max_push_targets() == 1
+    # ... and on 4 ranks one segment would have to feed 3 peers: the fused epilogue (2 targets)
+    # cannot, DistSpMV then exchanges through NCCL
+    full4 = [(25 * r, 25 * r + 25, 0, 100) for r in range(4)]
+    assert D.ExchangePlan(1, full4).max_push_targets() == 3
 
 
 class CpuShard:
