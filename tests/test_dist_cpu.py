@@ -135,3 +135,22 @@ def test_iterated_spmv_gloo(world, kind):
         assert nrecv >= 1
         if kind == "stencil" and world == 3 and rank == 1:
             assert [s[2] for s in segs] == [True, True, False]  # two boundary slabs + interior
+
+
+def test_row_cuts_equal_the_reference_partition_rule(O):
+    """With no alignment, balanced_row_cuts IS the reference's partition_csr_rows
+    (src/csr.c:218-276, restated and pinned in the oracle): same cut after every part, the
+    unused parts of a short matrix collapse onto M."""
+    from spmv_scpa_b200 import dist as D
+    rng = np.random.default_rng(0)
+    for _ in range(150):
+        M = int(rng.integers(1, 400))
+        lens = rng.integers(0, 30, M)
+        if rng.random() < 0.3:
+            lens[rng.integers(0, M)] = 5000       # a hub row
+        IRP = np.zeros(M + 1, np.int32)
+        IRP[1:] = np.cumsum(lens)
+        for parts in (1, 2, 3, 5, 8):
+            want = list(O.partition_rows(M, IRP, parts))
+            want += [M] * (parts + 1 - len(want))
+            assert list(D.balanced_row_cuts(IRP, parts, align=1)) == want
