@@ -19,6 +19,9 @@
  *   - threading: a handle is used by one thread at a time (launch plans are built lazily on
  *     first use of a kernel); different handles may be used concurrently; the reference-style
  *     entry points of cuda_csr.h / cuda_hll.h serialise on an internal lock.
+ *   - devices: the intended model is one process per GPU (spmv_b200_set_device once, early).
+ *     Handles remember their device; the scratch buffers of the reference-style entry points
+ *     and of spmv_b200_flush_l2 belong to the device that was current when first used.
  */
 #ifndef SPMV_B200_H
 #define SPMV_B200_H

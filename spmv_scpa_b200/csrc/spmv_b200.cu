@@ -54,6 +54,7 @@ thread_local int t_hll_wpb = 4; // reference default (src/cuda_hll.cu:12)
 int g_sm_count = 0;
 void *g_flush_buf = nullptr;
 constexpr size_t kFlushBytes = 512ull << 20; // > 126 MB L2
+constexpr int kMaxDevices = 64;
 
 int ensure_device() {
       static std::once_flag once;
@@ -469,7 +470,8 @@ int launch_stream_cfg(int cfg, const CsrArgs &a, const StreamPlan &sp) {
             auto kern = csr_stream_kernel<T, L, S, C, P, W, SP, OffT>;                             \
             using Cfg = StreamCfg<T, L, S, C, P, W, SP>;                                           \
             constexpr size_t smem = Cfg::template smem<OffT>();                                    \
-            static int occ = 0;                                                                    \
+            static int occ_by_dev[kMaxDevices] = {0}; /* the attribute is per device */            \
+            int &occ = occ_by_dev[a.h->device % kMaxDevices];                                      \
             if (!occ) {                                                                            \
                   B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                                  (int)smem));                                      \
@@ -963,6 +965,7 @@ extern "C" int spmv_b200_csr_time(spmv_b200_csr *h, int kernel, int wpb, const d
 
 struct spmv_b200_hll {
       long long M = 0, N = 0, NZ = 0, n_hacks = 0, slots = 0;
+      int device = 0;
       long long *d_hoff = nullptr;
       int *d_ja = nullptr;
       double *d_as = nullptr;
@@ -1081,7 +1084,8 @@ int hll_run(spmv_b200_hll *h, int kernel, int wpb, const double *d_x, double *d_
       case id: {                                                                                   \
             auto kern = hll_stream_kernel<W, S, C>;                                                \
             constexpr size_t smem = (size_t)S * C * 12 + S * 8 + 16;                               \
-            static int occ = 0;                                                                    \
+            static int occ_by_dev[kMaxDevices] = {0};                                              \
+            int &occ = occ_by_dev[h->device % kMaxDevices];                                        \
             if (!occ) {                                                                            \
                   B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                                  (int)smem));                                      \
@@ -1124,6 +1128,7 @@ extern "C" spmv_b200_hll *spmv_b200_hll_create(const sparse_hll *H, int is_col_m
             return nullptr;
       }
       auto *h = new spmv_b200_hll();
+      cudaGetDevice(&h->device);
       h->M = H->M, h->N = H->N, h->NZ = H->NZ, h->n_hacks = H->num_blocks;
       std::vector<int> width((size_t)h->n_hacks);
       std::vector<long long> src_off((size_t)h->n_hacks + 1, 0);
@@ -1193,6 +1198,7 @@ extern "C" spmv_b200_hll *spmv_b200_hll_from_csr(const spmv_b200_csr *A) {
             return nullptr;
       }
       auto *h = new spmv_b200_hll();
+      h->device = A->device;
       h->M = A->M, h->N = A->N, h->NZ = A->NZ;
       h->n_hacks = (A->M + kHack - 1) / kHack;
       std::vector<int> width((size_t)h->n_hacks, 0);
