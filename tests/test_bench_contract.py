@@ -49,3 +49,20 @@ def test_b200_arm_line():
     assert d["cpu_baseline"]["value"] > 0
     assert d["config"]["parity"]["csr"]["ok"] and d["config"]["parity"]["hll"]["ok"]
     assert "sm_mhz" in d["clocks"] and isinstance(d["clocks"]["reasons"], list)
+
+
+def test_reference_arm_under_torchrun_env():
+    """N>1: rank 0 alone prints the line, the other ranks exit 0 without work."""
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1", MASTER_ADDR="127.0.0.1", MASTER_PORT="29555")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
+                        "--workload", "tiny", "--steps", "2", "--warmup", "1"], capture_output=True, text=True,
+                       timeout=300, cwd=ROOT, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == ""
+    env["RANK"] = "0"
+    env["LOCAL_RANK"] = "0"
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
+                        "--workload", "tiny", "--steps", "2", "--warmup", "1"], capture_output=True, text=True,
+                       timeout=300, cwd=ROOT, env=env)
+    assert r.returncode == 0
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0
