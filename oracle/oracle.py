@@ -155,6 +155,67 @@ def hll_device_layout(M, IRP, JA, AS):
     return hoff, dja, das
 
 
+def sellp_layout(M, N, IRP, JA, AS, K, sigma, max_row):
+    """What libspmv_b200 must hold in HBM for the SELL-P form of this matrix
+    (spmv_scpa_b200/csrc/sell_kernels.cuh; no reference counterpart -- the rule restated here is the
+    one documented in that header, written independently in numpy):
+      panel p = columns [N*p//K, N*(p+1)//K); rows longer than max_row belong to no slice;
+      inside every window of `sigma` rows, rows are ordered by their entry count in the panel,
+      descending, ties by row index; slice = 32 consecutive rows of that order, width = count of
+      its first row; column-major with stride 32; pads: value 0.0, index = previous valid column
+      of the row inside the panel, or the panel's first column.
+    Returns soff[K, S+1], perm[K, S*32], ja[slots], as[slots]."""
+    IRP = np.asarray(IRP, np.int64)
+    JA = np.asarray(JA, np.int64)
+    AS = np.asarray(AS, np.float64)
+    S = (M + 31) // 32
+    pc = [N * p // K for p in range(K + 1)]
+    lens = np.diff(IRP)
+    perm = np.full((K, S * 32), -1, np.int32)
+    width = np.zeros((K, S), np.int64)
+    rows_entries = {}
+    for p in range(K):
+        cnt = np.zeros(M, np.int64)
+        for r in range(M):
+            if lens[r] > max_row:
+                cnt[r] = -1
+                continue
+            cols = JA[IRP[r]:IRP[r + 1]]
+            keep = np.nonzero((cols >= pc[p]) & (cols < pc[p + 1]))[0] if K > 1 else np.arange(len(cols))
+            rows_entries[(p, r)] = IRP[r] + keep
+            cnt[r] = len(keep)
+        for w0 in range(0, M, sigma):
+            w1 = min(M, w0 + sigma)
+            rows = [r for r in range(w0, w1) if cnt[r] >= 0]
+            rows.sort(key=lambda r: (-cnt[r], r))
+            perm[p, w0:w0 + len(rows)] = rows
+            for s in range(w0 // 32, (w1 + 31) // 32):
+                first = perm[p, s * 32]
+                width[p, s] = cnt[first] if first >= 0 else 0
+    soff = np.zeros((K, S + 1), np.int64)
+    run = 0
+    for p in range(K):
+        for s in range(S):
+            soff[p, s] = run
+            run += 32 * width[p, s]
+        soff[p, S] = run
+    ja = np.zeros(run, np.int32)
+    as_ = np.zeros(run, np.float64)
+    for p in range(K):
+        for s in range(S):
+            w = int(width[p, s])
+            blk_j = ja[soff[p, s]:soff[p, s + 1]].reshape(w, 32)
+            blk_a = as_[soff[p, s]:soff[p, s + 1]].reshape(w, 32)
+            for i in range(32):
+                r = perm[p, s * 32 + i]
+                ks = rows_entries[(p, r)] if r >= 0 else np.zeros(0, np.int64)
+                n = len(ks)
+                blk_j[:n, i] = JA[ks]
+                blk_a[:n, i] = AS[ks]
+                blk_j[n:, i] = JA[ks[-1]] if n else pc[p]
+    return soff, perm, ja, as_
+
+
 def csr_spmv(M, IRP, JA, AS, x):
     """y = A x, strict left-to-right FP64 (reference src/csr.c:201-216)."""
     IRP = np.ascontiguousarray(IRP)

@@ -128,12 +128,59 @@ _sig(b200, "spmv_b200_release_all", None)
 _sig(b200, "spmv_b200_set_timing", None, C.c_int, C.c_int)
 _sig(b200, "spmv_b200_counters", None, c_i64p, c_i64p, c_i64p)
 _sig(b200, "spmv_b200_set_knob", C.c_int, C.c_char_p, C.c_int)
+_sig(b200, "spmv_b200_host_register", C.c_int, vp, C.c_size_t)
+_sig(b200, "spmv_b200_host_unregister", C.c_int, vp)
+_sig(b200, "spmv_b200_set_cache_policy", C.c_int, C.c_int)
+_sig(b200, "spmv_b200_invalidate", None, vp)
+_sig(b200, "spmv_b200_csr_spmv_fused", C.c_int, vp, C.c_int, C.c_int, vp, vp, C.c_double, C.c_double,
+     vp, vp, vp, vp)
+_sig(b200, "spmv_b200_hll_spmv_fused", C.c_int, vp, C.c_int, C.c_int, vp, vp, C.c_double, C.c_double,
+     vp, vp, vp, vp)
+_sig(b200, "spmv_b200_csr_spmv_host", C.c_int, vp, C.c_int, C.c_int, vp, vp, c_dp)
+_sig(b200, "spmv_b200_hll_spmv_host", C.c_int, vp, C.c_int, C.c_int, vp, vp, c_dp)
+_sig(b200, "spmv_b200_csr_sell_info", C.c_int, vp, C.c_int, c_i64p, C.c_int)
+_sig(b200, "spmv_b200_hll_sell_info", C.c_int, vp, C.c_int, c_i64p, C.c_int)
+_sig(b200, "spmv_b200_sell_plan", C.c_int, c_ip, c_i64, C.c_int, C.c_int, c_ip, c_i64p)
+_sig(b200, "spmv_b200_csr_sell_download", C.c_int, vp, c_i64p, c_ip, c_ip, c_dp)
+
 _sig(b200, "spmv_b200_ipc_export", C.c_int, vp, _p(C.c_ubyte))
 _sig(b200, "spmv_b200_ipc_open", C.c_int, _p(C.c_ubyte), _p(vp))
 _sig(b200, "spmv_b200_ipc_close", C.c_int, vp)
 _sig(b200, "spmv_b200_enable_peer", C.c_int, C.c_int)
 _sig(b200, "spmv_b200_signal_peers", C.c_int, vp, C.c_int, _p(vp), vp)
 _sig(b200, "spmv_b200_wait_peers", C.c_int, vp, C.c_int, _p(vp), C.c_uint64, vp, vp)
+
+# multi-GPU iterated SpMV
+_sig(b200, "spmv_b200_partition_rows", C.c_int, c_i64, vp, C.c_int, C.c_int, C.c_int, c_i64p)
+_sig(b200, "spmv_b200_shard_scan", C.c_int, c_i64, c_i64, vp, C.c_int, c_ip, _p(S.shard_desc))
+_sig(b200, "spmv_b200_stencil27_shard_desc", C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+     _p(S.shard_desc))
+_sig(b200, "spmv_b200_dist_make_plan", C.c_int, C.c_int, C.c_int, _p(S.shard_desc), C.c_int,
+     _p(S.dist_plan))
+_sig(b200, "spmv_b200_dist_create", vp, _p(S.dist_plan), _p(S.shard_desc), vp, C.c_int, C.c_int)
+_sig(b200, "spmv_b200_dist_export", C.c_int, vp, _p(C.c_ubyte))
+_sig(b200, "spmv_b200_dist_connect", C.c_int, vp, _p(C.c_ubyte))
+_sig(b200, "spmv_b200_dist_set_x", C.c_int, vp, vp)
+_sig(b200, "spmv_b200_dist_iterate", C.c_int, vp, C.c_int)
+_sig(b200, "spmv_b200_dist_time", C.c_int, vp, C.c_int, C.c_int, c_dp)
+_sig(b200, "spmv_b200_dist_sync", C.c_int, vp)
+_sig(b200, "spmv_b200_dist_x", vp, vp)
+_sig(b200, "spmv_b200_dist_xlocal", vp, vp)
+_sig(b200, "spmv_b200_dist_get_x", C.c_int, vp, c_dp)
+_sig(b200, "spmv_b200_dist_stream", vp, vp)
+_sig(b200, "spmv_b200_dist_steps", c_i64, vp)
+_sig(b200, "spmv_b200_dist_mode", C.c_int, vp)
+_sig(b200, "spmv_b200_dist_has_graph", C.c_int, vp)
+_sig(b200, "spmv_b200_dist_destroy", None, vp)
+_sig(b200, "spmv_b200_dist_group_create", vp, _p(S.sparse_csr), C.c_int, C.c_int, C.c_int, C.c_int)
+_sig(b200, "spmv_b200_dist_group_stencil27", vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+     C.c_int)
+_sig(b200, "spmv_b200_dist_group_size", C.c_int, vp)
+_sig(b200, "spmv_b200_dist_group_rank", vp, vp, C.c_int)
+_sig(b200, "spmv_b200_dist_group_set_x", C.c_int, vp, c_dp)
+_sig(b200, "spmv_b200_dist_group_iterate", C.c_int, vp, C.c_int, c_dp)
+_sig(b200, "spmv_b200_dist_group_get_x", C.c_int, vp, c_dp)
+_sig(b200, "spmv_b200_dist_group_destroy", None, vp)
 
 # ---- host layer --------------------------------------------------------------
 _sig(host, "io_load_csr", vp, C.c_char_p)

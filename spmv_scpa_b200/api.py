@@ -25,6 +25,7 @@ from . import _lib as L
 from . import structs as S
 
 CSR_KERNEL_NAMES = ("thread_row", "warp_row", "adaptive", "block_row", "stream_tma")
+HOST_PIN = {}  # addresses page-locked through host_register()
 HLL_KERNEL_NAMES = ("thread_row_rm", "thread_row", "warp_hack_vec", "stream_tma")
 
 
@@ -281,6 +282,40 @@ def release_all():
     L.b200.spmv_b200_release_all()
 
 
+CACHE_POLICIES = {"off": 0, "hash": 1, "trust": 2}
+
+
+def set_cache_policy(policy):
+    """Matrix cache of the reference-style entry points: "off" (upload per call, like the
+    reference), "hash" (default: full content hash per call), "trust" (pointers + shape; call
+    invalidate() after editing a matrix in place)."""
+    rc = L.b200.spmv_b200_set_cache_policy(CACHE_POLICIES.get(policy, policy))
+    if rc:
+        raise ValueError(L.last_error())
+
+
+def invalidate(mat=None):
+    """Forget the device copy of one host matrix (CsrMatrix / HllMatrix), or of all."""
+    L.b200.spmv_b200_invalidate(None if mat is None else C.c_void_p(mat._addr))
+
+
+def pinned_empty(n, dtype=np.float64):
+    """numpy array in page-locked memory from spmv_b200_host_alloc (freed with pinned_free)."""
+    nbytes = n * np.dtype(dtype).itemsize
+    p = L.b200.spmv_b200_host_alloc(nbytes)
+    if not p:
+        raise MemoryError(L.last_error())
+    arr = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_ubyte)), shape=(max(nbytes, 1),))[:nbytes].view(dtype)
+    HOST_PIN[arr.ctypes.data] = p
+    return arr
+
+
+def pinned_free(arr):
+    p = HOST_PIN.pop(arr.ctypes.data, None)
+    if p:
+        L.b200.spmv_b200_host_free(p)
+
+
 def counters():
     a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
     L.b200.spmv_b200_counters(C.byref(a), C.byref(b), C.byref(c))
@@ -384,6 +419,46 @@ class CsrDevice:
                                                             r1, xp, yp, n, a0, a1, dst, st))
         return y
 
+    def spmv_fused(self, x, y, alpha=1.0, beta=0.0, z=None, w=None, dot=None, kernel=4,
+                   warps_per_block=4, stream=None):
+        """y = alpha*A x + beta*z and (if `dot`, a 1-element CUDA tensor, is given) dot[0] = sum y*w
+        in one pass over the matrix (spmv_b200_csr_spmv_fused)."""
+        zp = _dev_ptr(z, self.M, "z") if z is not None else None
+        wp = _dev_ptr(w, self.M, "w") if w is not None else None
+        dp = _dev_ptr(dot, 1, "dot") if dot is not None else None
+        self._check(L.b200.spmv_b200_csr_spmv_fused(self._h, kernel, warps_per_block, _dev_ptr(x, self.N, "x"),
+                                                    _dev_ptr(y, self.M, "y"), alpha, beta, zp, wp, dp,
+                                                    _stream_ptr(stream)))
+        return y
+
+    def spmv_host(self, x, y, kernel=4, warps_per_block=4):
+        """Host x (numpy, N) in, host y (numpy, M) out: upload, kernels and download pipelined
+        (spmv_b200_csr_spmv_host).  Returns the span of the kernels in ms."""
+        assert x.dtype == np.float64 and y.dtype == np.float64 and x.size >= self.N and y.size >= self.M
+        ms = C.c_double()
+        self._check(L.b200.spmv_b200_csr_spmv_host(self._h, kernel, warps_per_block, x.ctypes.data_as(C.c_void_p),
+                                                   y.ctypes.data_as(C.c_void_p), C.byref(ms)))
+        return ms.value
+
+    def sell_info(self, build=False):
+        out = (C.c_int64 * 8)()
+        self._check(L.b200.spmv_b200_csr_sell_info(self._h, int(build), out, 8))
+        keys = ("state", "panels", "sigma", "slices", "slots", "nnz_in_slices", "long_rows", "gather_span_ppm")
+        return dict(zip(keys, list(out)))
+
+    def sell_download(self):
+        info = self.sell_info()
+        assert info["state"] == 1, "no SELL-P plan on this handle"
+        K, S_, slots = info["panels"], info["slices"], info["slots"]
+        soff = np.zeros(K * (S_ + 1), np.int64)
+        perm = np.zeros(K * S_ * 32, np.int32)
+        ja = np.zeros(slots, np.int32)
+        as_ = np.zeros(slots, np.float64)
+        self._check(L.b200.spmv_b200_csr_sell_download(self._h, soff.ctypes.data_as(L.c_i64p),
+                                                       perm.ctypes.data_as(L.c_ip), ja.ctypes.data_as(L.c_ip),
+                                                       as_.ctypes.data_as(L.c_dp)))
+        return soff.reshape(K, S_ + 1), perm.reshape(K, S_ * 32), ja, as_
+
     def time(self, x, y, kernel=2, warps_per_block=4, warmup=3, reps=20, flush_l2=False, stream=None):
         """Per-launch milliseconds (CUDA events on the launching stream)."""
         ms = (C.c_double * reps)()
@@ -449,6 +524,29 @@ class HllDevice:
                                               _dev_ptr(x, self.N, "x"), _dev_ptr(y, self.M, "y"),
                                               _stream_ptr(stream)))
         return y
+
+    def spmv_fused(self, x, y, alpha=1.0, beta=0.0, z=None, w=None, dot=None, kernel=2,
+                   warps_per_block=4, stream=None):
+        zp = _dev_ptr(z, self.M, "z") if z is not None else None
+        wp = _dev_ptr(w, self.M, "w") if w is not None else None
+        dp = _dev_ptr(dot, 1, "dot") if dot is not None else None
+        self._check(L.b200.spmv_b200_hll_spmv_fused(self._h, kernel, warps_per_block, _dev_ptr(x, self.N, "x"),
+                                                    _dev_ptr(y, self.M, "y"), alpha, beta, zp, wp, dp,
+                                                    _stream_ptr(stream)))
+        return y
+
+    def spmv_host(self, x, y, kernel=2, warps_per_block=4):
+        assert x.dtype == np.float64 and y.dtype == np.float64 and x.size >= self.N and y.size >= self.M
+        ms = C.c_double()
+        self._check(L.b200.spmv_b200_hll_spmv_host(self._h, kernel, warps_per_block, x.ctypes.data_as(C.c_void_p),
+                                                   y.ctypes.data_as(C.c_void_p), C.byref(ms)))
+        return ms.value
+
+    def sell_info(self, build=False):
+        out = (C.c_int64 * 8)()
+        self._check(L.b200.spmv_b200_hll_sell_info(self._h, int(build), out, 8))
+        keys = ("state", "panels", "sigma", "slices", "slots", "nnz_in_slices", "long_rows", "gather_span_ppm")
+        return dict(zip(keys, list(out)))
 
     def time(self, x, y, kernel=2, warps_per_block=4, warmup=3, reps=20, flush_l2=False, stream=None):
         ms = (C.c_double * reps)()

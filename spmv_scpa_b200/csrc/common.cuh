@@ -198,23 +198,89 @@ __device__ __forceinline__ double group_sum(double v) {
       return v;
 }
 
-// Fused epilogue of the multi-GPU halo exchange: rows that a neighbouring
-// rank needs are also stored straight into that rank's halo buffer (peer
-// memory mapped through CUDA IPC, reached over NVLink).
-struct PushArgs {
-      int n;
+// ------------------------------------------------------------- epilogues --
+// What happens to a finished row sum is a compile-time choice (template flag
+// EPI of every kernel), so the single-GPU kernels carry none of the compares
+// the multi-GPU or fused variants need.
+//   EPI_PLAIN  y[row] = v
+//   EPI_PUSH   ... and rows a neighbouring rank needs are also stored straight
+//              into that rank's halo buffer (peer HBM mapped through CUDA IPC
+//              or peer access, reached over NVLink): the multi-GPU halo
+//              exchange fused into the SpMV epilogue
+//   EPI_ACC    y[row] += v  (column panels after the first one)
+//   EPI_FUSED  y[row] = alpha*v + beta*z[row], and sum_i y[i]*w[i] is
+//              accumulated per warp (iterated solvers: SpMV + axpby + dot in
+//              one pass over the matrix)
+constexpr int EPI_PLAIN = 0;
+constexpr int EPI_PUSH = 1;
+constexpr int EPI_ACC = 2;
+constexpr int EPI_FUSED = 3;
+
+struct EpiArgs {
+      // EPI_PUSH
+      int n_push;
       long long row0[2], row1[2];
       double *dst[2];
+      // EPI_FUSED (z, w, dot_partial may be null)
+      double alpha, beta;
+      const double *z, *w;
+      double *dot_partial; // one slot per warp of the launch
 };
 
-__device__ __forceinline__ void store_y(double *y, long long row, double v,
-                                        const PushArgs &push) {
-      y[row] = v;
-      if (push.n) {
+template <int EPI>
+__device__ __forceinline__ void store_y(double *y, long long row, double v, const EpiArgs &e,
+                                        double &dot_acc) {
+      if (EPI == EPI_ACC) {
+            y[row] += v;
+      } else if (EPI == EPI_FUSED) {
+            double r = e.alpha * v;
+            if (e.z)
+                  r = fma(e.beta, e.z[row], r);
+            y[row] = r;
+            if (e.w)
+                  dot_acc = fma(r, e.w[row], dot_acc);
+      } else {
+            y[row] = v;
+            if (EPI == EPI_PUSH) {
 #pragma unroll
-            for (int i = 0; i < 2; ++i)
-                  if (i < push.n && row >= push.row0[i] && row < push.row1[i])
-                        push.dst[i][row - push.row0[i]] = v;
+                  for (int i = 0; i < 2; ++i)
+                        if (i < e.n_push && row >= e.row0[i] && row < e.row1[i])
+                              e.dst[i][row - e.row0[i]] = v;
+            }
+      }
+}
+
+// End of a warp's work in an EPI_FUSED kernel: lane 0 publishes the warp's
+// partial dot product in slot `warp_slot` (deterministic: a fixed launch shape
+// gives a fixed summation tree; dot_reduce_kernel adds the slots in order).
+template <int EPI>
+__device__ __forceinline__ void epi_finish_warp(const EpiArgs &e, double dot_acc,
+                                                long long warp_slot) {
+      if (EPI == EPI_FUSED) {
+            if (e.dot_partial) {
+                  dot_acc = group_sum<32>(dot_acc);
+                  if ((threadIdx.x & 31) == 0)
+                        e.dot_partial[warp_slot] = dot_acc;
+            }
+      }
+}
+
+// out[0] = sum of partial[0..n), fixed order (one CTA, strided then tree).
+static __global__ void __launch_bounds__(1024)
+    dot_reduce_kernel(const double *__restrict__ partial, long long n, double *__restrict__ out) {
+      __shared__ double part[32];
+      double acc = 0.0;
+      for (long long i = threadIdx.x; i < n; i += blockDim.x)
+            acc += partial[i];
+      acc = group_sum<32>(acc);
+      if ((threadIdx.x & 31) == 0)
+            part[threadIdx.x >> 5] = acc;
+      __syncthreads();
+      if (threadIdx.x < 32) {
+            double v = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.0;
+            v = group_sum<32>(v);
+            if (threadIdx.x == 0)
+                  out[0] = v;
       }
 }
 

@@ -29,12 +29,13 @@ namespace b200 {
 // otherwise rows rowlist[0..nrows).  Rows longer than `max_len` are skipped
 // (they belong to another bin's launch); max_len < 0 disables the test.
 // ------------------------------------------------------------------------
-template <int LPR, typename OffT, bool HINTS>
+template <int LPR, typename OffT, int EPI>
 __global__ void __launch_bounds__(1024)
     csr_vec_kernel(const OffT *__restrict__ irp, const int *__restrict__ ja,
                    const double *__restrict__ as, long long row0, long long nrows,
                    const int *__restrict__ rowlist, long long max_len,
-                   const double *__restrict__ x, double *__restrict__ y, PushArgs push) {
+                   const double *__restrict__ x, double *__restrict__ y, EpiArgs epi) {
+      static_assert(EPI == EPI_PLAIN || EPI == EPI_PUSH, "direct kernels: plain or push epilogue");
       const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
       const long long g = gid / LPR;
       const int sub = (int)(gid % LPR);
@@ -62,15 +63,12 @@ __global__ void __launch_bounds__(1024)
                   const OffT kk = k + u * LPR;
                   const bool ok = kk < e;
                   okm[u] = ok;
-                  if (HINTS && LPR >= 16) {
+                  if (LPR >= 16) {
                         a[u] = ok ? ld_stream_f64(as + kk, pol_s) : 0.0;
                         c[u] = ok ? ld_stream_s32(ja + kk, pol_s) : 0;
-                  } else if (HINTS) {
+                  } else {
                         a[u] = ok ? ld_stream_l1_f64(as + kk, pol_s) : 0.0;
                         c[u] = ok ? ld_stream_l1_s32(ja + kk, pol_s) : 0;
-                  } else {
-                        a[u] = ok ? __ldg(as + kk) : 0.0;
-                        c[u] = ok ? __ldg(ja + kk) : 0;
                   }
             }
 #pragma unroll
@@ -84,8 +82,9 @@ __global__ void __launch_bounds__(1024)
       }
       double acc = acc0 + acc1;
       acc = group_sum<LPR>(acc);
+      double unused = 0.0;
       if (sub == 0)
-            store_y(y, row, acc, push);
+            store_y<EPI>(y, row, acc, epi, unused);
 }
 
 // Strided partial dot product of one long row: entries first, first+step, ...
@@ -126,12 +125,12 @@ __device__ __forceinline__ double long_row_partial(const double *__restrict__ as
 // One CTA per row (blockDim.x = 32*wpb).  Row = rowlist[blockIdx.x] or
 // row0 + blockIdx.x.
 // ------------------------------------------------------------------------
-template <typename OffT>
+template <typename OffT, int EPI>
 __global__ void __launch_bounds__(1024)
     csr_block_row_kernel(const OffT *__restrict__ irp, const int *__restrict__ ja,
                          const double *__restrict__ as, long long row0,
                          const int *__restrict__ rowlist, const double *__restrict__ x,
-                         double *__restrict__ y, PushArgs push) {
+                         double *__restrict__ y, EpiArgs epi) {
       __shared__ double warp_part[32];
       const long long row = rowlist ? (long long)rowlist[blockIdx.x] : row0 + blockIdx.x;
       const OffT s = irp[row], e = irp[row + 1];
@@ -149,8 +148,9 @@ __global__ void __launch_bounds__(1024)
       if (warp == 0) {
             double v = lane < nwarps ? warp_part[lane] : 0.0;
             v = group_sum<32>(v);
+            double unused = 0.0;
             if (lane == 0)
-                  store_y(y, row, v, push);
+                  store_y<EPI>(y, row, v, epi, unused);
       }
 }
 
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(1024)
 // row and produces partial[c]; csr_combine_kernel then adds the partials of
 // each split row in chunk order (deterministic, no atomics).
 // ------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
+static __global__ void __launch_bounds__(1024)
     csr_split_kernel(const long long *__restrict__ chunk_k0, const long long *__restrict__ chunk_k1,
                      const int *__restrict__ ja, const double *__restrict__ as,
                      const double *__restrict__ x, double *__restrict__ partial) {
@@ -182,17 +182,19 @@ __global__ void __launch_bounds__(1024)
       }
 }
 
+template <int EPI>
 __global__ void csr_combine_kernel(const int *__restrict__ split_row,
                                    const int *__restrict__ split_first_chunk, int n_split,
                                    const double *__restrict__ partial, double *__restrict__ y,
-                                   PushArgs push) {
+                                   EpiArgs epi) {
       const int i = blockIdx.x * blockDim.x + threadIdx.x;
       if (i >= n_split)
             return;
       double acc = 0.0;
       for (int c = split_first_chunk[i]; c < split_first_chunk[i + 1]; ++c)
             acc += partial[c];
-      store_y(y, split_row[i], acc, push);
+      double unused = 0.0;
+      store_y<EPI>(y, split_row[i], acc, epi, unused);
 }
 
 // ------------------------------------------------------------------------
@@ -237,14 +239,14 @@ struct StreamCfg {
 
 // All rows of one staged tile.  `gi` = row slot of this thread, `sub` = lane
 // within the row group.
-template <int LPR, int RPP, int PASSES, typename OffT>
+template <int LPR, int RPP, int PASSES, int EPI, typename OffT>
 __device__ __forceinline__ void stream_tile_rows(const OffT *__restrict__ irp,
                                                  const double *__restrict__ tas,
                                                  const int *__restrict__ tja, int r0, int r1,
                                                  long long kbase, int gi, int sub, long long ks,
                                                  long long ke, const double *__restrict__ x,
                                                  double *__restrict__ y, uint64_t pol_x,
-                                                 const PushArgs &push) {
+                                                 const EpiArgs &epi, double &dot_acc) {
       int row = r0 + gi;
 #pragma unroll 1
       for (int p = 0; p < PASSES; ++p) {
@@ -297,7 +299,7 @@ __device__ __forceinline__ void stream_tile_rows(const OffT *__restrict__ irp,
             if (LPR > 1)
                   acc = group_sum<LPR>(acc);
             if (sub == 0 && row < r1)
-                  store_y(y, row, acc, push);
+                  store_y<EPI>(y, row, acc, epi, dot_acc);
       }
 }
 
@@ -310,20 +312,19 @@ __device__ __forceinline__ void stream_tile_rows(const OffT *__restrict__ irp,
 //            than 32 entries are queued in shared memory instead;
 //   phase 3  warps drain the queue, one warp per long row, shuffle reduction.
 // Named barrier 1 (consumer threads only) separates the phases.
-template <int THREADS, int PASSES, int CAP, typename OffT>
+template <int THREADS, int PASSES, int CAP, int EPI, typename OffT>
 __device__ __forceinline__ void stream_tile_products(const OffT *s_irp, double *tas, const int *tja,
                                                      int r0, int r1, int r0a, long long kbase,
                                                      int cnt, int tid,
                                                      const double *__restrict__ x,
                                                      double *__restrict__ y, uint64_t pol_x,
-                                                     const PushArgs &push, int *s_queue,
-                                                     int *s_queue_n) {
+                                                     const EpiArgs &epi, double &dot_acc,
+                                                     int *s_queue, int *s_queue_n,
+                                                     int *s_queue_n_other) {
       // batches of up to 8 entries per thread (deeper batches measured slower:
       // profiles/r1_c4_*): loads, then gathers, then products back in place
       constexpr int PER = (CAP + THREADS - 1) / THREADS;
       constexpr int U = PER < 8 ? PER : 8;
-      if (tid == 0)
-            *s_queue_n = 0;
       for (int j = tid; j < cnt; j += THREADS * U) {
             double a[U], xv[U];
             int c[U];
@@ -344,6 +345,12 @@ __device__ __forceinline__ void stream_tile_products(const OffT *s_irp, double *
                         tas[j + u * THREADS] = a[u] * xv[u];
       }
       asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
+      // The long-row counter alternates between two words by tile parity.  Every thread is past
+      // the previous tile's phase 3 (its last reader) once it has crossed the barrier above, and
+      // the next tile's phase 2 (its next writer) lies behind that tile's first barrier, which
+      // this thread reaches only after this store: resetting it here races with nobody.
+      if (tid == 0)
+            *s_queue_n_other = 0;
 
 #pragma unroll 1
       for (int p = 0; p < PASSES; ++p) {
@@ -364,7 +371,7 @@ __device__ __forceinline__ void stream_tile_products(const OffT *s_irp, double *
                               acc0 += p0 + p2;
                               acc1 += p1 + p3;
                         }
-                        store_y(y, row, acc0 + acc1, push);
+                        store_y<EPI>(y, row, acc0 + acc1, epi, dot_acc);
                   } else {
                         s_queue[atomicAdd(s_queue_n, 1)] = row;
                   }
@@ -383,19 +390,20 @@ __device__ __forceinline__ void stream_tile_products(const OffT *s_irp, double *
                   acc += tas[j];
             acc = group_sum<32>(acc);
             if (lane == 0)
-                  store_y(y, row, acc, push);
+                  store_y<EPI>(y, row, acc, epi, dot_acc);
       }
       // the stage was written through the generic proxy; order those writes
       // before the bulk copy (async proxy) that refills it
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-template <int THREADS, int LPR, int STAGES, int CAP, int PASSES, bool WS, bool SPLIT, typename OffT>
+template <int THREADS, int LPR, int STAGES, int CAP, int PASSES, bool WS, bool SPLIT, int EPI,
+          typename OffT>
 __global__ void __launch_bounds__(THREADS + (WS ? 32 : 0))
     csr_stream_kernel(const OffT *__restrict__ irp, const int *__restrict__ ja,
                       const double *__restrict__ as, const int *__restrict__ tile_row,
                       const long long *__restrict__ tile_k, int tile0, int n_tiles,
-                      const double *__restrict__ x, double *__restrict__ y, PushArgs push) {
+                      const double *__restrict__ x, double *__restrict__ y, EpiArgs epi) {
       extern __shared__ __align__(128) unsigned char smem_raw[];
       double *s_as = reinterpret_cast<double *>(smem_raw);
       int *s_ja = reinterpret_cast<int *>(smem_raw + (size_t)STAGES * CAP * 8);
@@ -422,8 +430,11 @@ __global__ void __launch_bounds__(THREADS + (WS ? 32 : 0))
                   mbar_init(&empty[s], CWARPS);
             }
             mbar_fence_init();
+            if (SPLIT)
+                  s_queue_n[0] = s_queue_n[1] = 0;
       }
       __syncthreads();
+      double dot_acc = 0.0;
 
       const int first = tile0 + blockIdx.x;
       const int last = tile0 + n_tiles;
@@ -498,15 +509,15 @@ __global__ void __launch_bounds__(THREADS + (WS ? 32 : 0))
             if (SPLIT) {
                   const int cnt = (int)(((tile_k[t + 1] + 3) & ~3ll) - kbase);
                   if (staged)
-                        stream_tile_products<THREADS, PASSES, CAP, OffT>(
+                        stream_tile_products<THREADS, PASSES, CAP, EPI, OffT>(
                             s_irp + (size_t)stage * Cfg::kIrpSlots, s_as + (size_t)stage * CAP,
                             s_ja + (size_t)stage * CAP, r0, r1, r0 & ~(IRP_ALIGN - 1), kbase, cnt,
-                            tid, x, y, pol_x, push, s_queue, s_queue_n);
+                            tid, x, y, pol_x, epi, dot_acc, s_queue, s_queue_n + (it & 1),
+                            s_queue_n + ((it + 1) & 1));
             } else if (staged) {
-                  stream_tile_rows<LPR, RPP, PASSES, OffT>(irp, s_as + (size_t)stage * CAP,
-                                                           s_ja + (size_t)stage * CAP, r0, r1,
-                                                           kbase, gi, sub, ks, ke, x, y, pol_x,
-                                                           push);
+                  stream_tile_rows<LPR, RPP, PASSES, EPI, OffT>(
+                      irp, s_as + (size_t)stage * CAP, s_ja + (size_t)stage * CAP, r0, r1, kbase,
+                      gi, sub, ks, ke, x, y, pol_x, epi, dot_acc);
             }
             if (WS) {
                   __syncwarp();
@@ -521,6 +532,7 @@ __global__ void __launch_bounds__(THREADS + (WS ? 32 : 0))
                   }
             }
       }
+      epi_finish_warp<EPI>(epi, dot_acc, (long long)blockIdx.x * CWARPS + (tid >> 5));
 }
 
 } // namespace b200

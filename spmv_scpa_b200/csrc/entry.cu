@@ -1,0 +1,723 @@
+// entry.cu -- the reference's GPU boundary and everything that takes HOST buffers.
+//
+//   * csr_spmv_cuda_* / hll_spmv_cuda_* / set_*_warps_per_block (include/cuda_csr.h,
+//     include/cuda_hll.h), replacing reference src/cuda_csr.cu:210-371 and
+//     src/cuda_hll.cu:235-351: host A/H, host x in, host y out, kernel milliseconds returned;
+//   * timer_* with C linkage (include/cuda_timer.h; reference src/cuda_timer.cu:3-26);
+//   * the matrix cache behind those entry points (the reference uploads the matrix on every
+//     call, src/cuda_csr.cu:180-195; its driver then calls 27 variants on the same matrix,
+//     src/main.c:271-353);
+//   * the host-buffer pass shared by the entry points and spmv_b200_{csr,hll}_spmv_host():
+//     x goes up, row chunks compute and y comes back on three streams at once.
+#include "internal.cuh"
+
+#include <omp.h>
+
+using namespace b200;
+
+namespace {
+
+thread_local int t_csr_wpb = 4; // reference default (src/cuda_csr.cu:12)
+thread_local int t_hll_wpb = 4; // reference default (src/cuda_hll.cu:12)
+
+// ------------------------------------------------------------ per-device scratch
+constexpr int kMaxUnits = 64;
+
+struct DevScratch {
+      double *dx = nullptr, *dy = nullptr; // device x / y of the host-pointer calls
+      size_t cap_x = 0, cap_y = 0;
+      double *sx = nullptr, *sy = nullptr; // page-locked bounce buffers for pageable callers
+      size_t cap_sx = 0, cap_sy = 0;
+      cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
+      cudaEvent_t ev_in[kMaxUnits], ev_k[kMaxUnits], ev_out[kMaxUnits * 4], t0, t1;
+      bool ready = false;
+};
+DevScratch g_scratch[kMaxDevices];
+
+DevScratch *scratch() {
+      int dev = 0;
+      if (cudaGetDevice(&dev) != cudaSuccess)
+            return nullptr;
+      DevScratch &s = g_scratch[dev % kMaxDevices];
+      if (!s.ready) {
+            if (cudaStreamCreateWithFlags(&s.s_in, cudaStreamNonBlocking) != cudaSuccess ||
+                cudaStreamCreateWithFlags(&s.s_cmp, cudaStreamNonBlocking) != cudaSuccess ||
+                cudaStreamCreateWithFlags(&s.s_out, cudaStreamNonBlocking) != cudaSuccess) {
+                  fail(-EIO, "pipeline streams: %s", cudaGetErrorString(cudaGetLastError()));
+                  return nullptr;
+            }
+            for (int c = 0; c < kMaxUnits; ++c) {
+                  cudaEventCreateWithFlags(&s.ev_in[c], cudaEventDisableTiming);
+                  cudaEventCreateWithFlags(&s.ev_k[c], cudaEventDisableTiming);
+            }
+            for (int c = 0; c < kMaxUnits * 4; ++c)
+                  cudaEventCreateWithFlags(&s.ev_out[c], cudaEventDisableTiming);
+            cudaEventCreate(&s.t0);
+            cudaEventCreate(&s.t1);
+            s.ready = true;
+      }
+      return &s;
+}
+
+int grow_device(double **p, size_t *cap, size_t n) {
+      if (n <= *cap)
+            return 0;
+      cudaFree(*p);
+      *p = nullptr, *cap = 0;
+      B200_CUDA(cudaMalloc(p, (n + 32) * sizeof(double)));
+      *cap = n;
+      return 0;
+}
+int grow_pinned(double **p, size_t *cap, size_t n) {
+      if (n <= *cap)
+            return 0;
+      cudaFreeHost(*p);
+      *p = nullptr, *cap = 0;
+      B200_CUDA(cudaMallocHost(p, (n + 32) * sizeof(double)));
+      *cap = n;
+      return 0;
+}
+
+// Is this host pointer page-locked (cudaHostAlloc / cudaHostRegister)?  Only then can the copy
+// engines read it directly.
+bool is_pinned(const void *p) {
+      cudaPointerAttributes at{};
+      if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+      }
+      return at.type == cudaMemoryTypeHost;
+}
+
+// memcpy spread over the OpenMP team (pageable <-> bounce buffer)
+void parallel_copy(void *dst, const void *src, size_t bytes) {
+      constexpr size_t kBlock = 1u << 20;
+      const long long blocks = (long long)((bytes + kBlock - 1) / kBlock);
+      if (blocks <= 2) {
+            memcpy(dst, src, bytes);
+            return;
+      }
+#pragma omp parallel for schedule(static)
+      for (long long b = 0; b < blocks; ++b) {
+            const size_t off = (size_t)b * kBlock;
+            memcpy((char *)dst + off, (const char *)src + off, std::min(kBlock, bytes - off));
+      }
+}
+
+// ------------------------------------------------------------- host-buffer pass
+// One y = A x with host x and host y.  The work is described as `n` units; unit c needs
+// x[0, x_hi[c]) on the device (x_hi ascending), computes rows [row[c], row[c+1]) through
+// `launch(c, stream)`, and its slice of y can travel home as soon as it is done.  x is uploaded
+// in column order on one stream, the units run on a second one as their part of x arrives, y
+// slices go back on a third: PCIe carries both directions at once while the kernels run.
+// Page-locked caller buffers are used in place; pageable ones go through page-locked bounce
+// buffers with multi-threaded copies (a cudaHostRegister cache keyed on the caller's pointers
+// would be faster, but the reference frees and re-allocates y on every call --
+// compute_benchmark_csr, src/csr.c:182-199 -- and a registration that outlives its mapping
+// makes the copy engines read stale pages).
+// Returns the span of the units on the compute stream in ms (> 0), or <= 0 on error.
+template <typename Launch>
+double host_pass(long long N, long long M, const double *x, double *y, int n,
+                 const long long *x_hi, const long long *row, Launch &&launch) {
+      DevScratch *s = scratch();
+      if (!s || n < 1 || n > kMaxUnits)
+            return -1.0;
+      if (grow_device(&s->dx, &s->cap_x, (size_t)N) || grow_device(&s->dy, &s->cap_y, (size_t)M))
+            return -1.0;
+      const bool bounce_x = N > 0 && !is_pinned(x), bounce_y = M > 0 && !is_pinned(y);
+      if ((bounce_x && grow_pinned(&s->sx, &s->cap_sx, (size_t)N)) ||
+          (bounce_y && grow_pinned(&s->sy, &s->cap_sy, (size_t)M)))
+            return -1.0;
+
+      // kernels and downloads are queued first (they wait on events), so the host thread is
+      // free to feed the bounce buffer while they run
+      constexpr long long kPiece = 1ll << 20; // doubles per upload / download piece (8 MiB)
+      long long lo = 0;
+      struct Piece {
+            long long a, b;
+            int ev;
+      };
+      std::vector<Piece> downs;
+      int rc = 0, n_out = 0;
+      // 1. uploads of pinned x can be queued right away
+      auto upload_range = [&](long long a, long long b) {
+            for (long long p = a; p < b; p += kPiece) {
+                  const long long q = std::min(b, p + kPiece);
+                  const double *src = x + p;
+                  if (bounce_x) {
+                        parallel_copy(s->sx + p, x + p, (size_t)(q - p) * 8);
+                        src = s->sx + p;
+                  }
+                  cudaMemcpyAsync(s->dx + p, src, (size_t)(q - p) * 8, cudaMemcpyHostToDevice,
+                                  s->s_in);
+            }
+      };
+      if (!bounce_x) {
+            for (int c = 0; c < n; ++c) {
+                  if (x_hi[c] > lo)
+                        upload_range(lo, x_hi[c]);
+                  lo = std::max(lo, x_hi[c]);
+                  cudaEventRecord(s->ev_in[c], s->s_in);
+            }
+      }
+      // 2. with a bounce buffer the uploads are interleaved with the queueing of the units: a
+      //    unit can only be queued after its ev_in has been recorded
+      for (int c = 0; c < n && !rc; ++c) {
+            if (bounce_x) {
+                  if (x_hi[c] > lo)
+                        upload_range(lo, x_hi[c]);
+                  lo = std::max(lo, x_hi[c]);
+                  cudaEventRecord(s->ev_in[c], s->s_in);
+            }
+            cudaStreamWaitEvent(s->s_cmp, s->ev_in[c], 0);
+            if (c == 0)
+                  cudaEventRecord(s->t0, s->s_cmp);
+            if (row[c + 1] > row[c])
+                  rc = launch(c, s->s_cmp);
+            cudaEventRecord(s->ev_k[c], s->s_cmp);
+            cudaStreamWaitEvent(s->s_out, s->ev_k[c], 0);
+            for (long long p = row[c]; p < row[c + 1]; p += kPiece) {
+                  const long long q = std::min(row[c + 1], p + kPiece);
+                  double *dst = bounce_y ? s->sy + p : y + p;
+                  cudaMemcpyAsync(dst, s->dy + p, (size_t)(q - p) * 8, cudaMemcpyDeviceToHost,
+                                  s->s_out);
+                  if (bounce_y && n_out < kMaxUnits * 4) {
+                        cudaEventRecord(s->ev_out[n_out], s->s_out);
+                        downs.push_back({p, q, n_out++});
+                  } else if (bounce_y) {
+                        downs.push_back({p, q, -1}); // copied out after the final sync
+                  }
+            }
+      }
+      cudaEventRecord(s->t1, s->s_cmp);
+      // 3. drain the bounce buffer of y piece by piece while later pieces are still in flight
+      size_t late = downs.size();
+      for (size_t i = 0; i < downs.size() && !rc; ++i) {
+            if (downs[i].ev < 0) {
+                  late = i;
+                  break;
+            }
+            if (cudaEventSynchronize(s->ev_out[downs[i].ev]) != cudaSuccess)
+                  break;
+            parallel_copy(y + downs[i].a, s->sy + downs[i].a, (size_t)(downs[i].b - downs[i].a) * 8);
+      }
+      cudaError_t e1 = cudaStreamSynchronize(s->s_cmp), e2 = cudaStreamSynchronize(s->s_out),
+                  e3 = cudaStreamSynchronize(s->s_in);
+      if (rc)
+            return -1.0;
+      if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+            fail(-EIO, "host-buffer SpMV failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return -1.0;
+      }
+      for (size_t i = late; i < downs.size(); ++i)
+            parallel_copy(y + downs[i].a, s->sy + downs[i].a, (size_t)(downs[i].b - downs[i].a) * 8);
+      g_counters.h2d += N * 8;
+      g_counters.d2h += M * 8;
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, s->t0, s->t1);
+      return ms > 0.f ? (double)ms : 1e-6;
+}
+
+// Row chunks for the pipeline.  Usable when the matrix is banded enough that the first half of
+// the rows needs at most ~3/4 of x: then x can be uploaded in column order while earlier chunks
+// already compute and earlier parts of y already travel back.  C2 e2e measured 186 / 188 / 174
+// GFLOP/s with 4 / 8 / 16 chunks (profiles/r1_bench_c2_pipelined_e2e_K8.json); larger matrices
+// get proportionally more (one chunk per ~80 MB of matrix, 4..32).
+int pipe_chunks_for(long long NZ) {
+      if (g_knobs.pipe_chunks > 0)
+            return std::min(kMaxUnits, g_knobs.pipe_chunks);
+      const long long c = NZ * 12 / (80ll << 20);
+      return (int)std::max<long long>(4, std::min<long long>(32, c));
+}
+
+void build_pipe(spmv_b200_csr *h) {
+      h->pipe_state = -1;
+      const int chunks = pipe_chunks_for(h->NZ);
+      if (h->M < chunks * 4096ll || h->NZ < (1 << 22))
+            return;
+      std::vector<long long> cut((size_t)chunks + 1, 0);
+      for (int c = 1; c < chunks; ++c) {
+            const long long want = h->NZ / chunks * c;
+            long long r = std::lower_bound(h->h_irp.begin(), h->h_irp.end(), want) - h->h_irp.begin();
+            r = std::min(h->M, (r + 31) / 32 * 32);
+            cut[c] = std::max(r, cut[c - 1]);
+      }
+      cut[chunks] = h->M;
+      std::vector<long long> hi((size_t)chunks, 0);
+      long long running = 0;
+      for (int c = 0; c < chunks; ++c) {
+            int mx = -1;
+            if (csr_max_col(h, h->h_irp[cut[c]], h->h_irp[cut[c + 1]], &mx))
+                  return;
+            running = std::max(running, (long long)mx + 1);
+            hi[c] = running;
+      }
+      hi[chunks - 1] = h->N; // whatever is left of x goes up with the last block
+      if (hi[chunks / 2 - 1] * 4 > h->N * 3)
+            return; // not banded: the first half of the rows already needs (almost) all of x
+      for (int c = 0; c < chunks; ++c) {
+            Segment sg;
+            sg.r0 = cut[c], sg.r1 = cut[c + 1];
+            if (build_adaptive(h, sg))
+                  return;
+            h->pipe_segs.push_back(sg);
+      }
+      h->pipe_x_hi = hi;
+      h->pipe_state = 1;
+}
+
+void build_pipe(spmv_b200_hll *h) {
+      h->pipe_state = -1;
+      const int chunks = pipe_chunks_for(h->slots);
+      if (h->n_hacks < chunks * 128ll || h->slots < (1 << 22))
+            return;
+      std::vector<long long> cut((size_t)chunks + 1, 0);
+      for (int c = 1; c < chunks; ++c) {
+            const long long want = h->slots / chunks * c;
+            long long b = std::lower_bound(h->h_hoff.begin(), h->h_hoff.end(), want) - h->h_hoff.begin();
+            cut[c] = std::max(std::min(b, h->n_hacks), cut[c - 1]);
+      }
+      cut[chunks] = h->n_hacks;
+      std::vector<long long> hi((size_t)chunks, 0);
+      long long running = 0;
+      for (int c = 0; c < chunks; ++c) {
+            int mx = -1;
+            if (hll_max_col(h, cut[c], cut[c + 1], &mx))
+                  return;
+            running = std::max(running, (long long)mx + 1);
+            hi[c] = running;
+      }
+      hi[chunks - 1] = h->N;
+      if (hi[chunks / 2 - 1] * 4 > h->N * 3)
+            return;
+      h->pipe_hack = cut;
+      h->pipe_x_hi = hi;
+      h->pipe_state = 1;
+}
+
+double csr_host_spmv(spmv_b200_csr *h, int kernel, int wpb, const double *x, double *y) {
+      if (!x || !y) {
+            fail(-EINVAL, "null x or y");
+            return -1.0;
+      }
+      wpb = clamp_wpb(wpb);
+      DevScratch *s = scratch();
+      if (!s)
+            return -1.0;
+      const bool chunkable = kernel == SPMV_B200_CSR_ADAPTIVE || kernel == SPMV_B200_CSR_STREAM;
+      if (g_knobs.pipeline && chunkable && h->pipe_state == 0)
+            build_pipe(h);
+      if (g_knobs.pipeline && chunkable && h->pipe_state == 1) {
+            const int n = (int)h->pipe_segs.size();
+            std::vector<long long> row((size_t)n + 1);
+            for (int c = 0; c < n; ++c)
+                  row[c] = h->pipe_segs[c].r0;
+            row[n] = h->M;
+            return host_pass(h->N, h->M, x, y, n, h->pipe_x_hi.data(), row.data(),
+                             [&](int c, cudaStream_t st) {
+                                   return csr_run_segment(h, h->pipe_segs[c], kernel, wpb, s->dx,
+                                                          s->dy, EPI_PLAIN, EpiArgs{}, st);
+                             });
+      }
+      // not banded (or not a chunkable kernel): one unit that needs all of x
+      const long long x_hi[1] = {h->N}, row[2] = {0, h->M};
+      return host_pass(h->N, h->M, x, y, 1, x_hi, row, [&](int, cudaStream_t st) {
+            return csr_run(h, kernel, wpb, 0, h->M, s->dx, s->dy, EPI_PLAIN, EpiArgs{}, st);
+      });
+}
+
+double hll_host_spmv(spmv_b200_hll *h, int kernel, int wpb, const double *x, double *y) {
+      if (!x || !y) {
+            fail(-EINVAL, "null x or y");
+            return -1.0;
+      }
+      wpb = clamp_wpb(wpb);
+      DevScratch *s = scratch();
+      if (!s)
+            return -1.0;
+      const bool chunkable = kernel != SPMV_B200_HLL_STREAM;
+      if (g_knobs.pipeline && chunkable && h->pipe_state == 0)
+            build_pipe(h);
+      if (g_knobs.pipeline && chunkable && h->pipe_state == 1) {
+            const int n = (int)h->pipe_hack.size() - 1;
+            std::vector<long long> row((size_t)n + 1);
+            for (int c = 0; c <= n; ++c)
+                  row[c] = std::min(h->M, h->pipe_hack[c] * kHack);
+            return host_pass(h->N, h->M, x, y, n, h->pipe_x_hi.data(), row.data(),
+                             [&](int c, cudaStream_t st) {
+                                   return hll_run_range(h, kernel, wpb, h->pipe_hack[c],
+                                                        h->pipe_hack[c + 1], s->dx, s->dy,
+                                                        EPI_PLAIN, EpiArgs{}, st);
+                             });
+      }
+      const long long x_hi[1] = {h->N}, row[2] = {0, h->M};
+      return host_pass(h->N, h->M, x, y, 1, x_hi, row, [&](int, cudaStream_t st) {
+            return hll_run_range(h, kernel, wpb, 0, h->n_hacks, s->dx, s->dy, EPI_PLAIN, EpiArgs{},
+                                 st);
+      });
+}
+
+// ------------------------------------------------------------------ the cache
+// Policy (knob "cache" / SPMV_B200_CACHE / spmv_b200_set_cache_policy):
+//   0 off    upload on every call, like the reference (src/cuda_csr.cu:180-205)
+//   1 hash   keep the device copy, but re-hash the caller's arrays IN FULL on every call and
+//            re-upload when anything changed (default: an in-place edit of one value is seen)
+//   2 trust  key on the host pointers and the shape only; the caller promises to call
+//            spmv_b200_invalidate() after editing a matrix in place
+
+// 64-bit content hash of a byte range, computed in parallel over 1 MiB blocks.
+uint64_t hash_block(const unsigned char *b, size_t bytes) {
+      uint64_t h0 = 0x9E3779B97F4A7C15ull, h1 = 0xC2B2AE3D27D4EB4Full, h2 = 0x165667B19E3779F9ull,
+               h3 = 0x27D4EB2F165667C5ull;
+      size_t i = 0;
+      for (; i + 32 <= bytes; i += 32) {
+            uint64_t v[4];
+            memcpy(v, b + i, 32);
+            h0 = (h0 ^ v[0]) * 0xBF58476D1CE4E5B9ull;
+            h1 = (h1 ^ v[1]) * 0x94D049BB133111EBull;
+            h2 = (h2 ^ v[2]) * 0xD6E8FEB86659FD93ull;
+            h3 = (h3 ^ v[3]) * 0xFF51AFD7ED558CCDull;
+            h0 ^= h0 >> 29, h1 ^= h1 >> 31, h2 ^= h2 >> 30, h3 ^= h3 >> 28;
+      }
+      uint64_t tail = bytes;
+      for (; i < bytes; ++i)
+            tail = tail * 1099511628211ull ^ b[i];
+      uint64_t h = h0 ^ (h1 * 3) ^ (h2 * 5) ^ (h3 * 7) ^ tail;
+      h ^= h >> 33;
+      h *= 0xFF51AFD7ED558CCDull;
+      return h ^ (h >> 33);
+}
+
+uint64_t full_hash(const void *p, size_t bytes) {
+      if (!p || !bytes)
+            return bytes;
+      constexpr size_t kBlock = 1u << 20;
+      const long long blocks = (long long)((bytes + kBlock - 1) / kBlock);
+      uint64_t acc = 0;
+#pragma omp parallel for schedule(static) reduction(^ : acc)
+      for (long long b = 0; b < blocks; ++b) {
+            const size_t off = (size_t)b * kBlock;
+            const uint64_t hb = hash_block((const unsigned char *)p + off, std::min(kBlock, bytes - off));
+            // position-dependent combination (xor of rotated, index-mixed block hashes)
+            const uint64_t m = (hb + 0x9E3779B97F4A7C15ull * (uint64_t)(b + 1));
+            acc ^= (m << (b % 63 + 1)) | (m >> (64 - (b % 63 + 1)));
+      }
+      return acc ^ bytes;
+}
+
+struct CsrEntry {
+      const void *A, *irp, *ja, *as;
+      int M, N, NZ;
+      uint64_t fp;
+      spmv_b200_csr *h;
+};
+struct HllEntry {
+      const void *H, *blocks;
+      int M, N, NZ, col_major;
+      uint64_t fp;
+      spmv_b200_hll *h;
+};
+
+std::mutex g_cache_mu;
+std::vector<CsrEntry> g_csr_cache;
+std::vector<HllEntry> g_hll_cache;
+constexpr size_t kCacheSlots = 4;
+
+uint64_t csr_fp(const sparse_csr *A) {
+      if (g_knobs.cache != 1)
+            return 0;
+      return full_hash(A->IRP, ((size_t)A->M + 1) * 4) ^ (full_hash(A->JA, (size_t)A->NZ * 4) * 3) ^
+             (full_hash(A->AS, (size_t)A->NZ * 8) * 5);
+}
+
+spmv_b200_csr *cached_csr(const sparse_csr *A) {
+      if (g_knobs.cache == 0) { // reference behaviour: a fresh upload per call
+            for (auto &e : g_csr_cache)
+                  spmv_b200_csr_destroy(e.h);
+            g_csr_cache.clear();
+      }
+      const uint64_t fp = csr_fp(A);
+      for (size_t i = 0; i < g_csr_cache.size(); ++i) {
+            auto &e = g_csr_cache[i];
+            if (e.A == A && e.irp == A->IRP && e.ja == A->JA && e.as == A->AS && e.M == A->M &&
+                e.N == A->N && e.NZ == A->NZ) {
+                  if (e.fp == fp)
+                        return e.h;
+                  spmv_b200_csr_destroy(e.h); // same arrays, edited in place
+                  g_csr_cache.erase(g_csr_cache.begin() + (long)i);
+                  break;
+            }
+      }
+      spmv_b200_csr *h = spmv_b200_csr_create(A);
+      if (!h)
+            return nullptr;
+      if (g_csr_cache.size() >= kCacheSlots) {
+            spmv_b200_csr_destroy(g_csr_cache.front().h);
+            g_csr_cache.erase(g_csr_cache.begin());
+      }
+      g_csr_cache.push_back({A, A->IRP, A->JA, A->AS, A->M, A->N, A->NZ, fp, h});
+      return h;
+}
+
+uint64_t hll_fp(const sparse_hll *H) {
+      if (g_knobs.cache != 1)
+            return 0;
+      uint64_t f = full_hash(H->blocks, (size_t)H->num_blocks * sizeof(ellpack_block));
+      const long long nb = H->num_blocks;
+      uint64_t acc = 0;
+#pragma omp parallel for schedule(static, 64) reduction(^ : acc)
+      for (long long i = 0; i < nb; ++i) {
+            const ellpack_block &b = H->blocks[i];
+            const size_t n = (size_t)b.M * b.max_NZ;
+            const uint64_t hb = hash_block((const unsigned char *)b.JA, n * 4) * 3 ^
+                                hash_block((const unsigned char *)b.AS, n * 8) * 5;
+            const uint64_t m = hb + 0x9E3779B97F4A7C15ull * (uint64_t)(i + 1);
+            acc ^= (m << (i % 63 + 1)) | (m >> (64 - (i % 63 + 1)));
+      }
+      return f ^ acc;
+}
+
+spmv_b200_hll *cached_hll(const sparse_hll *H, int col_major) {
+      if (g_knobs.cache == 0) {
+            for (auto &e : g_hll_cache)
+                  spmv_b200_hll_destroy(e.h);
+            g_hll_cache.clear();
+      }
+      const uint64_t fp = hll_fp(H);
+      for (size_t i = 0; i < g_hll_cache.size(); ++i) {
+            auto &e = g_hll_cache[i];
+            if (e.H == H && e.blocks == H->blocks && e.M == H->M && e.N == H->N && e.NZ == H->NZ &&
+                e.col_major == col_major) {
+                  if (e.fp == fp)
+                        return e.h;
+                  spmv_b200_hll_destroy(e.h);
+                  g_hll_cache.erase(g_hll_cache.begin() + (long)i);
+                  break;
+            }
+      }
+      spmv_b200_hll *h = spmv_b200_hll_create(H, col_major);
+      if (!h)
+            return nullptr;
+      if (g_hll_cache.size() >= kCacheSlots) {
+            spmv_b200_hll_destroy(g_hll_cache.front().h);
+            g_hll_cache.erase(g_hll_cache.begin());
+      }
+      g_hll_cache.push_back({H, H->blocks, H->M, H->N, H->NZ, col_major, fp, h});
+      return h;
+}
+
+// Returned duration: the reference returns the time of its single kernel launch
+// (src/cuda_csr.cu:224-233).  Here y comes from one host-buffer pass; the returned value is the
+// median of g_knobs.reps separately timed launches on the resident x (or, with reps = 0, the
+// span of the kernels inside the pass).
+template <typename Timed>
+double finish_entry(double pass_ms, Timed &&timed) {
+      if (pass_ms <= 0.0)
+            return -1.0;
+      if (g_knobs.reps <= 0)
+            return pass_ms;
+      std::vector<double> ms((size_t)g_knobs.reps);
+      if (timed(ms.data()))
+            return -1.0;
+      const double med = median_of(ms);
+      return med > 0.0 ? med : 1e-6; // an empty matrix launches nothing: timer resolution
+}
+
+double csr_entry(const sparse_csr *A, const double *x, double *y, int kernel) {
+      if (!A) {
+            fail(-EINVAL, "null sparse_csr");
+            return -1.0;
+      }
+      if (ensure_device())
+            return -1.0;
+      std::lock_guard<std::mutex> lk(g_cache_mu);
+      spmv_b200_csr *h = cached_csr(A);
+      if (!h)
+            return -1.0;
+      const int wpb = clamp_wpb(t_csr_wpb);
+      const double pass_ms = csr_host_spmv(h, kernel, wpb, x, y);
+      DevScratch *s = scratch();
+      return finish_entry(pass_ms, [&](double *ms) {
+            return spmv_b200_csr_time(h, kernel, wpb, s->dx, s->dy, std::max(0, g_knobs.warmup - 1),
+                                      g_knobs.reps, 0, ms, nullptr);
+      });
+}
+
+double hll_entry(const sparse_hll *H, const double *x, double *y, int kernel, int col_major) {
+      if (!H) {
+            fail(-EINVAL, "null sparse_hll");
+            return -1.0;
+      }
+      if (ensure_device())
+            return -1.0;
+      std::lock_guard<std::mutex> lk(g_cache_mu);
+      spmv_b200_hll *h = cached_hll(H, col_major);
+      if (!h)
+            return -1.0;
+      const int wpb = clamp_wpb(t_hll_wpb);
+      const double pass_ms = hll_host_spmv(h, kernel, wpb, x, y);
+      DevScratch *s = scratch();
+      return finish_entry(pass_ms, [&](double *ms) {
+            return spmv_b200_hll_time(h, kernel, wpb, s->dx, s->dy, std::max(0, g_knobs.warmup - 1),
+                                      g_knobs.reps, 0, ms, nullptr);
+      });
+}
+
+} // namespace
+
+// ------------------------------------------------------- handle-level host calls
+extern "C" int spmv_b200_csr_spmv_host(spmv_b200_csr *h, int kernel, int wpb, const double *x,
+                                       double *y, double *kernel_ms) {
+      if (!h)
+            return fail(-EINVAL, "null CSR handle");
+      const double ms = csr_host_spmv(h, kernel, wpb, x, y);
+      if (kernel_ms)
+            *kernel_ms = ms;
+      return ms > 0.0 ? 0 : -EIO;
+}
+
+extern "C" int spmv_b200_hll_spmv_host(spmv_b200_hll *h, int kernel, int wpb, const double *x,
+                                       double *y, double *kernel_ms) {
+      if (!h)
+            return fail(-EINVAL, "null HLL handle");
+      const double ms = hll_host_spmv(h, kernel, wpb, x, y);
+      if (kernel_ms)
+            *kernel_ms = ms;
+      return ms > 0.0 ? 0 : -EIO;
+}
+
+extern "C" int spmv_b200_host_register(void *ptr, size_t bytes) {
+      if (ensure_device())
+            return -ENODEV;
+      B200_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+      return 0;
+}
+extern "C" int spmv_b200_host_unregister(void *ptr) {
+      B200_CUDA(cudaHostUnregister(ptr));
+      return 0;
+}
+
+// ------------------------------------------------------------- cache control
+extern "C" void spmv_b200_release_all(void) {
+      std::lock_guard<std::mutex> lk(g_cache_mu);
+      for (auto &e : g_csr_cache)
+            spmv_b200_csr_destroy(e.h);
+      for (auto &e : g_hll_cache)
+            spmv_b200_hll_destroy(e.h);
+      g_csr_cache.clear();
+      g_hll_cache.clear();
+      for (auto &s : g_scratch) {
+            cudaFree(s.dx), cudaFree(s.dy);
+            cudaFreeHost(s.sx), cudaFreeHost(s.sy);
+            s.dx = s.dy = s.sx = s.sy = nullptr;
+            s.cap_x = s.cap_y = s.cap_sx = s.cap_sy = 0;
+      }
+      cudaGetLastError();
+}
+
+extern "C" void spmv_b200_invalidate(const void *matrix) {
+      std::lock_guard<std::mutex> lk(g_cache_mu);
+      for (size_t i = 0; i < g_csr_cache.size();) {
+            if (!matrix || g_csr_cache[i].A == matrix) {
+                  spmv_b200_csr_destroy(g_csr_cache[i].h);
+                  g_csr_cache.erase(g_csr_cache.begin() + (long)i);
+            } else {
+                  ++i;
+            }
+      }
+      for (size_t i = 0; i < g_hll_cache.size();) {
+            if (!matrix || g_hll_cache[i].H == matrix) {
+                  spmv_b200_hll_destroy(g_hll_cache[i].h);
+                  g_hll_cache.erase(g_hll_cache.begin() + (long)i);
+            } else {
+                  ++i;
+            }
+      }
+}
+
+extern "C" int spmv_b200_set_cache_policy(int policy) {
+      if (policy < 0 || policy > 2)
+            return fail(-EINVAL, "cache policy must be 0 (off), 1 (hash) or 2 (trust)");
+      std::lock_guard<std::mutex> lk(g_cache_mu);
+      g_knobs.cache = policy;
+      return 0;
+}
+
+// ============================================ reference-style entry points
+extern "C" void set_csr_warps_per_block(int wppb) { t_csr_wpb = wppb; }
+extern "C" void set_hll_warps_per_block(int wppb) { t_hll_wpb = wppb; }
+
+extern "C" double csr_spmv_cuda_thread_row(const sparse_csr *A, const double *x, double *y,
+                                           void *) {
+      return csr_entry(A, x, y, SPMV_B200_CSR_THREAD_ROW);
+}
+extern "C" double csr_spmv_cuda_warp_row(const sparse_csr *A, const double *x, double *y,
+                                         void *) {
+      return csr_entry(A, x, y, SPMV_B200_CSR_WARP_ROW);
+}
+extern "C" double csr_spmv_cuda_halfwarp_row(const sparse_csr *A, const double *x, double *y,
+                                             void *) {
+      return csr_entry(A, x, y, SPMV_B200_CSR_ADAPTIVE);
+}
+extern "C" double csr_spmv_cuda_block_row(const sparse_csr *A, const double *x, double *y,
+                                          void *) {
+      return csr_entry(A, x, y, SPMV_B200_CSR_BLOCK_ROW);
+}
+extern "C" double csr_spmv_cuda_halfwarp_row_text(const sparse_csr *A, const double *x, double *y,
+                                                  void *) {
+      return csr_entry(A, x, y, SPMV_B200_CSR_STREAM);
+}
+
+extern "C" double hll_spmv_cuda_threads_row_major(const sparse_hll *H, const double *x, double *y,
+                                                  void *) {
+      return hll_entry(H, x, y, SPMV_B200_HLL_THREAD_ROW_RM, /*col_major=*/0);
+}
+extern "C" double hll_spmv_cuda_threads_col_major(const sparse_hll *H, const double *x, double *y,
+                                                  void *) {
+      return hll_entry(H, x, y, SPMV_B200_HLL_THREAD_ROW, /*col_major=*/1);
+}
+extern "C" double hll_spmv_cuda_warp_block(const sparse_hll *H, const double *x, double *y,
+                                           void *) {
+      return hll_entry(H, x, y, SPMV_B200_HLL_WARP_HACK, /*col_major=*/1);
+}
+extern "C" double hll_spmv_cuda_halfwarp_row(const sparse_hll *H, const double *x, double *y,
+                                             void *) {
+      return hll_entry(H, x, y, SPMV_B200_HLL_STREAM, /*col_major=*/0);
+}
+
+// ================================================================== timer
+// C-linkage stopwatch (reference: include/cuda_timer.cuh, src/cuda_timer.cu).
+
+extern "C" int timer_init(cuda_timer *t) {
+      if (!t || ensure_device())
+            return -1;
+      cudaEvent_t a, b;
+      if (cudaEventCreate(&a) != cudaSuccess)
+            return -1;
+      if (cudaEventCreate(&b) != cudaSuccess) {
+            cudaEventDestroy(a);
+            return -1;
+      }
+      t->start = a, t->stop = b;
+      return 0;
+}
+extern "C" void timer_start(cuda_timer *t, void *stream) {
+      cudaEventRecord((cudaEvent_t)t->start, as_stream(stream));
+}
+extern "C" double timer_stop(cuda_timer *t, void *stream) {
+      float ms = 0.f;
+      if (cudaEventRecord((cudaEvent_t)t->stop, as_stream(stream)) != cudaSuccess ||
+          cudaEventSynchronize((cudaEvent_t)t->stop) != cudaSuccess ||
+          cudaEventElapsedTime(&ms, (cudaEvent_t)t->start, (cudaEvent_t)t->stop) != cudaSuccess) {
+            fail(-EIO, "timer_stop: %s", cudaGetErrorString(cudaGetLastError()));
+            return -1.0;
+      }
+      return (double)ms;
+}
+extern "C" void timer_destroy(cuda_timer *t) {
+      if (!t)
+            return;
+      cudaEventDestroy((cudaEvent_t)t->start);
+      cudaEventDestroy((cudaEvent_t)t->stop);
+      t->start = t->stop = nullptr;
+}

@@ -28,14 +28,17 @@
 
 namespace b200 {
 
-template <int VEC, bool HINTS>
+template <int VEC, int EPI>
 __global__ void __launch_bounds__(1024)
     hll_warp_kernel(const long long *__restrict__ hoff, const int *__restrict__ ja,
-                    const double *__restrict__ as, long long n_hacks, long long M,
-                    const double *__restrict__ x, double *__restrict__ y, PushArgs push) {
-      const long long h = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+                    const double *__restrict__ as, long long hack0, long long n_hacks, long long M,
+                    const double *__restrict__ x, double *__restrict__ y, EpiArgs epi) {
+      static_assert(EPI == EPI_PLAIN || (EPI == EPI_FUSED && VEC == 1), "HLL epilogues");
+      const long long wslot = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+      const long long h = hack0 + wslot;
       if (h >= n_hacks)
             return; // whole warp
+      double dot_acc = 0.0;
       const int lane = threadIdx.x & 31;
       const long long base = hoff[h];
       const int width = (int)((hoff[h + 1] - base) >> 5);
@@ -57,13 +60,8 @@ __global__ void __launch_bounds__(1024)
                         const int s = (j + u) * 32 + lane;
                         const bool ok = j + u < width;
                         okm[u] = ok;
-                        if (HINTS) {
-                              a[u] = ok ? ld_stream_f64(has + s, pol_s) : 0.0;
-                              c[u] = ok ? ld_stream_s32(hja + s, pol_s) : 0;
-                        } else {
-                              a[u] = ok ? __ldg(has + s) : 0.0;
-                              c[u] = ok ? __ldg(hja + s) : 0;
-                        }
+                        a[u] = ok ? ld_stream_f64(has + s, pol_s) : 0.0;
+                        c[u] = ok ? ld_stream_s32(hja + s, pol_s) : 0;
                   }
 #pragma unroll
                   for (int u = 0; u < U; ++u)
@@ -76,7 +74,8 @@ __global__ void __launch_bounds__(1024)
             }
             const double acc = acc0 + acc1;
             if (row_base + lane < M)
-                  store_y(y, row_base + lane, acc, push);
+                  store_y<EPI>(y, row_base + lane, acc, epi, dot_acc);
+            epi_finish_warp<EPI>(epi, dot_acc, wslot);
       } else if (VEC == 2) {
             // lane L: rows 2*(L&15), +1 ; slot columns j + (L>>4), step 2
             const int sub = lane & 15, half = lane >> 4;
@@ -94,9 +93,9 @@ __global__ void __launch_bounds__(1024)
             if (half == 0) {
                   const long long r = row_base + 2 * sub;
                   if (r < M)
-                        store_y(y, r, acc0, push);
+                        store_y<EPI>(y, r, acc0, epi, dot_acc);
                   if (r + 1 < M)
-                        store_y(y, r + 1, acc1, push);
+                        store_y<EPI>(y, r + 1, acc1, epi, dot_acc);
             }
       } else {
             // lane L: rows 4*(L&7) .. +3 ; slot columns j + (L>>3), step 4
@@ -122,13 +121,13 @@ __global__ void __launch_bounds__(1024)
             if (quarter == 0) {
                   const long long r = row_base + 4 * sub;
                   if (r < M)
-                        store_y(y, r, acc0, push);
+                        store_y<EPI>(y, r, acc0, epi, dot_acc);
                   if (r + 1 < M)
-                        store_y(y, r + 1, acc1, push);
+                        store_y<EPI>(y, r + 1, acc1, epi, dot_acc);
                   if (r + 2 < M)
-                        store_y(y, r + 2, acc2, push);
+                        store_y<EPI>(y, r + 2, acc2, epi, dot_acc);
                   if (r + 3 < M)
-                        store_y(y, r + 3, acc3, push);
+                        store_y<EPI>(y, r + 3, acc3, epi, dot_acc);
             }
       }
 }
@@ -143,8 +142,9 @@ template <int WARPS, int STAGES, int CAP>
 __global__ void __launch_bounds__(WARPS * 32)
     hll_stream_kernel(const long long *__restrict__ hoff, const int *__restrict__ ja,
                       const double *__restrict__ as, const int *__restrict__ tile_h, int n_tiles,
-                      long long M, const double *__restrict__ x, double *__restrict__ y,
-                      PushArgs push) {
+                      long long M, const double *__restrict__ x, double *__restrict__ y) {
+      const EpiArgs epi{};
+      double dot_acc = 0.0;
       extern __shared__ __align__(128) unsigned char smem_raw[];
       double *s_as = reinterpret_cast<double *>(smem_raw);
       int *s_ja = reinterpret_cast<int *>(smem_raw + (size_t)STAGES * CAP * 8);
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(WARPS * 32)
                         const double acc = acc0 + acc1;
                         const long long r = (long long)h * kHack + lane;
                         if (r < M)
-                              store_y(y, r, acc, push);
+                              store_y<EPI_PLAIN>(y, r, acc, epi, dot_acc);
                   }
             } else {
                   // one oversized hack: all warps share its slot columns
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(WARPS * 32)
                               v += big_part[w][lane];
                         const long long r = (long long)h0 * kHack + lane;
                         if (r < M)
-                              store_y(y, r, v, push);
+                              store_y<EPI_PLAIN>(y, r, v, epi, dot_acc);
                   }
             }
             __syncthreads();
@@ -290,7 +290,8 @@ template <typename OffT>
 __global__ void hll_fill_from_csr_kernel(const OffT *__restrict__ irp, const int *__restrict__ cja,
                                          const double *__restrict__ cas, long long M,
                                          long long n_hacks, const long long *__restrict__ hoff,
-                                         int *__restrict__ ja, double *__restrict__ as) {
+                                         int *__restrict__ ja, double *__restrict__ as,
+                                         int *__restrict__ rowlen) {
       const long long h = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
       if (h >= n_hacks)
             return;
@@ -304,6 +305,7 @@ __global__ void hll_fill_from_csr_kernel(const OffT *__restrict__ irp, const int
             k0 = irp[r];
             len = (int)(irp[r + 1] - k0);
       }
+      rowlen[r] = len; // allocated for n_hacks * 32 rows
       int last_col = 0;
       for (int j = 0; j < width; ++j) {
             double a = 0.0;
@@ -324,7 +326,8 @@ __global__ void hll_fill_from_host_layout_kernel(const long long *__restrict__ s
                                                  const double *__restrict__ src_as,
                                                  int col_major, long long M, long long n_hacks,
                                                  const long long *__restrict__ hoff,
-                                                 int *__restrict__ ja, double *__restrict__ as) {
+                                                 int *__restrict__ ja, double *__restrict__ as,
+                                                 int *__restrict__ rowlen) {
       const long long h = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
       if (h >= n_hacks)
             return;
@@ -335,7 +338,7 @@ __global__ void hll_fill_from_host_layout_kernel(const long long *__restrict__ s
       const int rows = rows_left < kHack ? (int)rows_left : kHack;
       const int *sja = src_ja + src_off[h];
       const double *sas = src_as + src_off[h];
-      int last_col = 0;
+      int last_col = 0, len = 0;
       for (int j = 0; j < width; ++j) {
             double a = 0.0;
             if (lane < rows) {
@@ -343,14 +346,17 @@ __global__ void hll_fill_from_host_layout_kernel(const long long *__restrict__ s
                                                 : (long long)lane * width + j;
                   const int c = sja[s];
                   a = sas[s];
-                  if (c != -1)
+                  if (c != -1) {
                         last_col = c;
-                  else
+                        len = j + 1; // the host packer fills a row left to right (src/hll.c:78-91)
+                  } else {
                         a = 0.0;
+                  }
             }
             as[base + (long long)j * 32 + lane] = a;
             ja[base + (long long)j * 32 + lane] = last_col;
       }
+      rowlen[h * kHack + lane] = len;
 }
 
 } // namespace b200

@@ -1,60 +1,26 @@
-// spmv_b200.cu -- libspmv_b200: C ABI, resident matrices, launch plans.
+// spmv_b200.cu -- libspmv_b200 core: resident matrices, launch plans, kernel launchers and the
+// handle API of include/spmv_b200.h.
 //
-// Exports
-//   * the reference's GPU boundary (include/cuda_csr.h, include/cuda_hll.h,
-//     include/cuda_timer.h), replacing reference src/cuda_csr.cu,
-//     src/cuda_hll.cu and src/cuda_timer.cu;
-//   * the handle API of include/spmv_b200.h.
-// There is no CPU fallback anywhere in this file: without a usable GPU every
-// entry point fails loudly.
-#include <algorithm>
-#include <cerrno>
-#include <cstdlib>
-#include <cstring>
-#include <map>
-#include <mutex>
-#include <numeric>
-#include <vector>
+// The other translation units: entry.cu (the reference's GPU boundary -- include/cuda_csr.h,
+// include/cuda_hll.h, include/cuda_timer.h -- replacing reference src/cuda_csr.cu,
+// src/cuda_hll.cu and src/cuda_timer.cu, plus the host-buffer pipelines) and dist.cu (multi-GPU
+// iterated SpMV).  There is no CPU fallback anywhere: without a usable GPU every entry point
+// fails loudly.
+#include "internal.cuh"
 
 #include "csr_kernels.cuh"
 #include "gen_kernels.cuh"
 #include "hll_kernels.cuh"
-
-extern "C" {
-#include "cuda_csr.h"
-#include "cuda_hll.h"
-#include "cuda_timer.h"
-#include "spmv_b200.h"
-}
+#include "sell_kernels.cuh"
 
 using namespace b200;
 
 // ===================================================================== state
-namespace {
+namespace b200 {
 
-struct Counters {
-      long long launches = 0, h2d = 0, d2h = 0;
-} g_counters;
-
-struct Knobs {
-      int stream_hints = 1; // matrix streams: L1 no_allocate + L2 evict_first
-      int csr_stream_cfg = -1; // -1: pick from warps_per_block
-      int hll_vec = -1;        // vector width of the HLL headline kernel; -1 = by size of x
-      int hll_stream_cfg = -1;
-      int regular_lpr = -1; // force lanes-per-row (log2) of the adaptive base launch
-      int force_wide = 0;   // use 64-bit row offsets even when NZ < 2^31 (tests)
-      int adaptive_direct = 0; // 1: the adaptive path never uses the TMA-staged kernel
-      int pipeline = 1;        // host-buffer pipeline in the reference-style CSR entry points
-      int warmup = 1, reps = 3;
-} g_knobs;
-
-thread_local int t_csr_wpb = 4; // reference default (src/cuda_csr.cu:12)
-thread_local int t_hll_wpb = 4; // reference default (src/cuda_hll.cu:12)
-
+Counters g_counters;
+Knobs g_knobs;
 int g_sm_count = 0;
-void *g_flush_buf = nullptr;
-constexpr size_t kFlushBytes = 512ull << 20; // > 126 MB L2
-constexpr int kMaxDevices = 64;
 
 int ensure_device() {
       static std::once_flag once;
@@ -72,6 +38,14 @@ int ensure_device() {
                   g_knobs.warmup = std::max(0, atoi(env));
             if ((env = getenv("SPMV_B200_REPS")))
                   g_knobs.reps = std::max(1, atoi(env));
+            if ((env = getenv("SPMV_B200_CACHE"))) {
+                  if (!strcmp(env, "off") || !strcmp(env, "0"))
+                        g_knobs.cache = 0;
+                  else if (!strcmp(env, "trust") || !strcmp(env, "2"))
+                        g_knobs.cache = 2;
+                  else
+                        g_knobs.cache = 1;
+            }
       });
       if (rc)
             return rc;
@@ -88,101 +62,21 @@ int ensure_device() {
       return 0;
 }
 
-inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+// (An L2 access-policy window that pins part of a large x was tried in round 1 and removed:
+// reserving the persisting carve-out shrinks the L2 left for everything else -- C2 dropped from
+// 97 % to 89 % of peak -- and C3/C4, whose gathers it was meant to help, did not move at all:
+// profiles/r1_kbench_c3_l2window_{on,off}.txt.  The per-load evict_last / evict_first policies
+// and, for x larger than the L2, the column panels of sell_kernels.cuh are what is used.)
 
-template <typename T>
-int upload(T **d, const std::vector<T> &h) {
-      *d = nullptr;
-      if (h.empty())
-            return 0;
-      B200_CUDA(cudaMalloc(d, h.size() * sizeof(T)));
-      B200_CUDA(cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
-      g_counters.h2d += (long long)(h.size() * sizeof(T));
-      return 0;
-}
-
-inline int blocks_for(long long threads, int block) {
-      return (int)((threads + block - 1) / block);
-}
-
-inline int clamp_wpb(int wpb) { return wpb < 1 ? 1 : (wpb > 32 ? 32 : wpb); }
-
-// (An L2 access-policy window that pins part of a large x was tried and removed: reserving
-// the persisting carve-out shrinks the L2 left for everything else -- C2 dropped from 97 % to
-// 89 % of peak -- and C3/C4, whose gathers it was meant to help, did not move at all:
-// profiles/r1_kbench_c3_l2window_{on,off}.txt.  The per-load evict_last / evict_first
-// policies are what the kernels use.)
-
-} // namespace
-
-// ================================================================ CSR handle
+} // namespace b200
 
 namespace {
-
-// adaptive bins by row length
-constexpr int kNumKinds = 8; // 0..5: 2^k lanes per row, 6: CTA per row, 7: split
-constexpr long long kKindMax[kNumKinds] = {4, 8, 16, 32, 64, 2048, 65536, -1};
-constexpr long long kSplitChunk = 32768;
-
-inline int kind_of(long long len) {
-      for (int k = 0; k < kNumKinds - 1; ++k)
-            if (len <= kKindMax[k])
-                  return k;
-      return kNumKinds - 1;
-}
-
-struct RowList {
-      int *d_rows = nullptr;
-      long long n = 0;
-};
-
-struct SplitPlan {
-      long long *d_k0 = nullptr, *d_k1 = nullptr;
-      int *d_row = nullptr, *d_first = nullptr;
-      double *d_partial = nullptr;
-      int n_rows = 0, n_chunks = 0;
-};
-
-struct StreamPlan {
-      int *d_tile_row = nullptr;
-      long long *d_tile_k = nullptr;
-      int n_tiles = 0;
-      RowList long_lists[kNumKinds]; // rows that do not fit a stage, by kind (5..7)
-      SplitPlan split;
-      bool built = false;
-};
-
-struct Segment {
-      long long r0 = 0, r1 = 0;
-      // adaptive plan
-      bool regular = false;
-      int base_kind = 0;
-      RowList lists[kNumKinds];
-      SplitPlan split;
-      long long kind_rows[kNumKinds] = {0};
-      // stream plans, one per kernel configuration
-      std::map<int, StreamPlan> stream;
-};
-
+void *g_flush_buf[kMaxDevices] = {nullptr};
+constexpr size_t kFlushBytes = 512ull << 20; // > 126 MB L2
 } // namespace
 
-struct spmv_b200_csr {
-      long long M = 0, N = 0, NZ = 0, col_offset = 0;
-      bool wide = false; // 64-bit row offsets
-      void *d_irp = nullptr;
-      int *d_ja = nullptr;
-      double *d_as = nullptr;
-      std::vector<long long> h_irp; // host copy of the row offsets (planning)
-      std::vector<Segment> segs;
-      int device = 0;
-      // host-buffer pipeline of the reference-style entry points (banded matrices): row chunks
-      // with their own launch plans, and how much of x each chunk needs to have arrived
-      std::vector<Segment> pipe_segs;
-      std::vector<long long> pipe_x_hi; // x[0, pipe_x_hi[c]) must be on the device before chunk c
-      int pipe_state = 0;               // 0 not tried, 1 usable, -1 not worth it
-};
-
-namespace {
+// ================================================================ CSR plans
+namespace b200 {
 
 void free_list(RowList &l) {
       cudaFree(l.d_rows);
@@ -193,8 +87,27 @@ void free_split(SplitPlan &s) {
           cudaFree(s.d_partial);
       s = SplitPlan();
 }
+void free_sell(SellPlan &sp) {
+      cudaFree(sp.d_soff), cudaFree(sp.d_perm), cudaFree(sp.d_ja), cudaFree(sp.d_as);
+      free_list(sp.long_block);
+      free_split(sp.long_split);
+      sp = SellPlan();
+}
+void free_segment(Segment &sg) {
+      for (auto &l : sg.lists)
+            free_list(l);
+      free_split(sg.split);
+      for (auto &kv : sg.stream) {
+            cudaFree(kv.second.d_tile_row);
+            cudaFree(kv.second.d_tile_k);
+            for (auto &l : kv.second.long_lists)
+                  free_list(l);
+            free_split(kv.second.split);
+      }
+      sg.stream.clear();
+}
 
-int build_split(const spmv_b200_csr *h, const std::vector<int> &rows, SplitPlan &sp) {
+static int build_split(const spmv_b200_csr *h, const std::vector<int> &rows, SplitPlan &sp) {
       std::vector<long long> k0, k1;
       std::vector<int> first;
       for (int r : rows) {
@@ -219,7 +132,8 @@ int build_split(const spmv_b200_csr *h, const std::vector<int> &rows, SplitPlan 
       return 0;
 }
 
-// Classify the rows of one segment into length bins.
+// Classify the rows of one segment into length bins (counts only; the per-bin row lists are
+// built on first use of the direct binned kernels, build_bin_lists).
 int build_adaptive(spmv_b200_csr *h, Segment &sg) {
       const long long rows = sg.r1 - sg.r0;
       std::fill(sg.kind_rows, sg.kind_rows + kNumKinds, 0);
@@ -243,7 +157,12 @@ int build_adaptive(spmv_b200_csr *h, Segment &sg) {
             sg.regular = true;
             sg.base_kind = g_knobs.regular_lpr;
       }
+      return 0;
+}
 
+static int build_bin_lists(spmv_b200_csr *h, Segment &sg) {
+      if (sg.lists_built)
+            return 0;
       std::vector<int> lists[kNumKinds];
       for (long long r = sg.r0; r < sg.r1; ++r) {
             const int k = kind_of(h->h_irp[r + 1] - h->h_irp[r]);
@@ -263,11 +182,12 @@ int build_adaptive(spmv_b200_csr *h, Segment &sg) {
                         return rc;
             }
       }
+      sg.lists_built = true;
       return 0;
 }
 
 // Tiles of consecutive rows for the TMA-staged kernel.
-int build_stream(spmv_b200_csr *h, Segment &sg, int max_rows, int cap, StreamPlan &sp) {
+static int build_stream(spmv_b200_csr *h, Segment &sg, int max_rows, int cap, StreamPlan &sp) {
       std::vector<int> tile_row;
       std::vector<long long> tile_k;
       std::vector<int> longs[kNumKinds];
@@ -302,7 +222,7 @@ int build_stream(spmv_b200_csr *h, Segment &sg, int max_rows, int cap, StreamPla
       return rc;
 }
 
-int finish_create(spmv_b200_csr *h, const long long *cuts, int n_cuts) {
+static int finish_create(spmv_b200_csr *h, const long long *cuts, int n_cuts) {
       std::vector<long long> bounds;
       bounds.push_back(0);
       for (int i = 0; i < n_cuts; ++i)
@@ -324,16 +244,32 @@ int finish_create(spmv_b200_csr *h, const long long *cuts, int n_cuts) {
       return 0;
 }
 
-// ------------------------------------------------------------- launchers --
+} // namespace b200
+
+// ================================================================ launchers
+namespace {
 
 struct CsrArgs {
       const spmv_b200_csr *h;
       const double *x;
       double *y;
-      PushArgs push;
+      int epi_mode; // EPI_PLAIN / EPI_PUSH / EPI_FUSED
+      EpiArgs epi;
       cudaStream_t st;
       int threads;
 };
+
+// The direct (non-staged) kernels exist with the plain and the push epilogue only.
+#define DIRECT_EPI_SWITCH(mode, STMT)                                                              \
+      do {                                                                                         \
+            if ((mode) == EPI_PUSH) {                                                              \
+                  constexpr int E = EPI_PUSH;                                                      \
+                  STMT;                                                                            \
+            } else {                                                                               \
+                  constexpr int E = EPI_PLAIN;                                                     \
+                  STMT;                                                                            \
+            }                                                                                      \
+      } while (0)
 
 template <int LPR, typename OffT>
 void launch_vec_t(const CsrArgs &a, long long row0, long long nrows, const int *list,
@@ -342,12 +278,9 @@ void launch_vec_t(const CsrArgs &a, long long row0, long long nrows, const int *
             return;
       const int grid = blocks_for(nrows * LPR, a.threads);
       const OffT *irp = static_cast<const OffT *>(a.h->d_irp);
-      if (g_knobs.stream_hints)
-            csr_vec_kernel<LPR, OffT, true><<<grid, a.threads, 0, a.st>>>(
-                irp, a.h->d_ja, a.h->d_as, row0, nrows, list, max_len, a.x, a.y, a.push);
-      else
-            csr_vec_kernel<LPR, OffT, false><<<grid, a.threads, 0, a.st>>>(
-                irp, a.h->d_ja, a.h->d_as, row0, nrows, list, max_len, a.x, a.y, a.push);
+      DIRECT_EPI_SWITCH(a.epi_mode, (csr_vec_kernel<LPR, OffT, E><<<grid, a.threads, 0, a.st>>>(
+                                        irp, a.h->d_ja, a.h->d_as, row0, nrows, list, max_len, a.x,
+                                        a.y, a.epi)));
       ++g_counters.launches;
 }
 
@@ -369,9 +302,10 @@ void launch_block_rows(const CsrArgs &a, long long row0, long long nrows, const 
       if (nrows <= 0)
             return;
       // gridDim.x limit is 2^31-1, enough for any row count we accept
-      csr_block_row_kernel<OffT><<<(unsigned)nrows, a.threads, 0, a.st>>>(
-          static_cast<const OffT *>(a.h->d_irp), a.h->d_ja, a.h->d_as, row0, list, a.x, a.y,
-          a.push);
+      DIRECT_EPI_SWITCH(a.epi_mode,
+                        (csr_block_row_kernel<OffT, E><<<(unsigned)nrows, a.threads, 0, a.st>>>(
+                            static_cast<const OffT *>(a.h->d_irp), a.h->d_ja, a.h->d_as, row0, list,
+                            a.x, a.y, a.epi)));
       ++g_counters.launches;
 }
 
@@ -380,8 +314,9 @@ void launch_split(const CsrArgs &a, const SplitPlan &sp) {
             return;
       csr_split_kernel<<<sp.n_chunks, 512, 0, a.st>>>(sp.d_k0, sp.d_k1, a.h->d_ja, a.h->d_as, a.x,
                                                       sp.d_partial);
-      csr_combine_kernel<<<blocks_for(sp.n_rows, 128), 128, 0, a.st>>>(
-          sp.d_row, sp.d_first, sp.n_rows, sp.d_partial, a.y, a.push);
+      DIRECT_EPI_SWITCH(a.epi_mode,
+                        (csr_combine_kernel<E><<<blocks_for(sp.n_rows, 128), 128, 0, a.st>>>(
+                            sp.d_row, sp.d_first, sp.n_rows, sp.d_partial, a.y, a.epi)));
       g_counters.launches += 2;
 }
 
@@ -410,84 +345,84 @@ void run_adaptive(const CsrArgs &a, const Segment &sg) {
       launch_split(a, sg.split);
 }
 
-// stream kernel configurations:
-// {consumer threads, lanes/row, stages, cap, passes, warp-specialised, entry-split}
+// Stream kernel configurations reachable from stream_cfg_for() (the ids are those of the
+// round-1 sweeps under profiles/, 35 shapes were tried; these seven won their class):
+// {id, consumer threads, lanes/row, stages, cap, passes, entry-split}.  All warp-specialised.
 #define STREAM_CONFIGS(X)                                                                          \
-      X(0, 128, 1, 2, 4096, 1, false, false)                                                       \
-      X(1, 256, 2, 2, 3584, 1, false, false)                                                       \
-      X(2, 256, 1, 2, 8192, 1, false, false)                                                       \
-      X(3, 256, 2, 2, 4096, 1, false, false)                                                       \
-      X(4, 128, 1, 2, 4096, 4, false, false)                                                       \
-      X(5, 64, 1, 3, 2048, 1, false, false)                                                        \
-      X(6, 512, 4, 2, 4096, 1, false, false)                                                       \
-      X(7, 512, 2, 2, 8192, 1, false, false)                                                       \
-      X(8, 256, 4, 2, 2048, 1, false, false)                                                       \
-      X(9, 256, 2, 3, 3584, 1, false, false)                                                       \
-      X(10, 256, 2, 2, 4096, 1, true, false)                                                       \
-      X(11, 256, 2, 3, 3584, 1, true, false)                                                       \
-      X(12, 512, 4, 2, 4096, 1, true, false)                                                       \
-      X(13, 512, 2, 2, 8192, 1, true, false)                                                       \
-      X(14, 128, 1, 3, 4096, 1, true, false)                                                       \
-      X(15, 256, 1, 2, 8192, 1, true, false)                                                       \
-      X(16, 256, 2, 4, 2048, 1, true, false)                                                       \
-      X(17, 128, 1, 2, 4096, 4, true, false)                                                       \
-      X(18, 256, 1, 2, 4096, 4, true, false)                                                       \
-      X(19, 256, 1, 2, 8192, 4, true, false)                                                       \
-      X(20, 256, 1, 2, 4096, 4, true, true)                                                        \
-      X(21, 512, 1, 2, 4096, 2, true, true)                                                        \
-      X(22, 256, 1, 3, 2048, 4, true, true)                                                        \
-      X(23, 512, 1, 2, 8192, 2, true, true)                                                        \
-      X(24, 256, 1, 2, 4096, 8, true, true)                                                        \
-      X(25, 512, 1, 3, 4096, 2, true, true)                                                        \
-      X(26, 512, 1, 4, 2048, 2, true, true)                                                        \
-      X(27, 512, 1, 6, 2048, 2, true, true)                                                        \
-      X(28, 256, 1, 4, 2048, 4, true, true)                                                        \
-      X(29, 512, 1, 4, 1024, 2, true, true)                                                        \
-      X(30, 512, 1, 8, 1024, 2, true, true)                                                        \
-      X(31, 128, 1, 2, 1024, 8, true, true)                                                        \
-      X(32, 128, 1, 3, 1024, 8, true, true)                                                        \
-      X(33, 256, 1, 2, 2048, 4, true, true)                                                        \
-      X(34, 256, 1, 2, 1024, 4, true, true)
-constexpr int kNumStreamCfg = 35;
+      X(10, 256, 2, 2, 4096, 1, false)                                                             \
+      X(12, 512, 4, 2, 4096, 1, false)                                                             \
+      X(13, 512, 2, 2, 8192, 1, false)                                                             \
+      X(24, 256, 1, 2, 4096, 8, true)                                                              \
+      X(25, 512, 1, 3, 4096, 2, true)                                                              \
+      X(26, 512, 1, 4, 2048, 2, true)                                                              \
+      X(33, 256, 1, 2, 2048, 4, true)
 
 struct StreamShape {
-      int threads, lpr, stages, cap, passes;
+      int id, threads, lpr, stages, cap, passes;
 };
-constexpr StreamShape kStreamShapes[kNumStreamCfg] = {
-#define X(id, t, l, s, c, p, w, sp) {t, l, s, c, p},
+constexpr StreamShape kStreamShapes[] = {
+#define X(id, t, l, s, c, p, sp) {id, t, l, s, c, p},
     STREAM_CONFIGS(X)
 #undef X
 };
+const StreamShape *stream_shape(int cfg) {
+      for (const auto &s : kStreamShapes)
+            if (s.id == cfg)
+                  return &s;
+      return nullptr;
+}
 
+template <typename Kern>
+int stream_occupancy(Kern kern, int threads, size_t smem, int device, int *occ_cache) {
+      int &occ = occ_cache[device % kMaxDevices];
+      if (!occ) {
+            B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem));
+            B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+            if (occ < 1)
+                  return fail(-EINVAL, "stream kernel does not fit on an SM");
+      }
+      return 0;
+}
+
+// One launch of the staged kernel over the tiles of `sp`.  *grid_out = CTAs launched.
 template <typename OffT>
-int launch_stream_cfg(int cfg, const CsrArgs &a, const StreamPlan &sp) {
+int launch_stream_cfg(int cfg, const CsrArgs &a, const StreamPlan &sp, int *grid_out) {
+      if (grid_out)
+            *grid_out = 0;
       if (sp.n_tiles <= 0)
             return 0;
       const OffT *irp = static_cast<const OffT *>(a.h->d_irp);
       switch (cfg) {
-#define X(id, T, L, S, C, P, W, SP)                                                                \
-      case id: {                                                                                   \
-            auto kern = csr_stream_kernel<T, L, S, C, P, W, SP, OffT>;                             \
-            using Cfg = StreamCfg<T, L, S, C, P, W, SP>;                                           \
+#define LAUNCH_ONE(E, T, L, S, C, P, SP)                                                           \
+      {                                                                                            \
+            auto kern = csr_stream_kernel<T, L, S, C, P, true, SP, E, OffT>;                       \
+            using Cfg = StreamCfg<T, L, S, C, P, true, SP>;                                        \
             constexpr size_t smem = Cfg::template smem<OffT>();                                    \
             static int occ_by_dev[kMaxDevices] = {0}; /* the attribute is per device */            \
-            int &occ = occ_by_dev[a.h->device % kMaxDevices];                                      \
-            if (!occ) {                                                                            \
-                  B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                                 (int)smem));                                      \
-                  B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern,              \
-                                                                          Cfg::kThreads, smem));   \
-                  if (occ < 1)                                                                     \
-                        return fail(-EINVAL, "stream cfg %d does not fit on an SM", id);           \
-            }                                                                                      \
-            const int grid = std::min(sp.n_tiles, occ * g_sm_count);                               \
+            int rc = stream_occupancy(kern, Cfg::kThreads, smem, a.h->device, occ_by_dev);         \
+            if (rc)                                                                                \
+                  return rc;                                                                       \
+            const int grid =                                                                       \
+                std::min(sp.n_tiles, occ_by_dev[a.h->device % kMaxDevices] * g_sm_count);          \
             kern<<<grid, Cfg::kThreads, smem, a.st>>>(irp, a.h->d_ja, a.h->d_as, sp.d_tile_row,    \
                                                       sp.d_tile_k, 0, sp.n_tiles, a.x, a.y,        \
-                                                      a.push);                                     \
-            break;                                                                                 \
+                                                      a.epi);                                      \
+            if (grid_out)                                                                          \
+                  *grid_out = grid;                                                                \
       }
+#define X(id, T, L, S, C, P, SP)                                                                   \
+      case id:                                                                                     \
+            if (a.epi_mode == EPI_PUSH)                                                            \
+                  LAUNCH_ONE(EPI_PUSH, T, L, S, C, P, SP)                                          \
+            else if (a.epi_mode == EPI_FUSED)                                                      \
+                  LAUNCH_ONE(EPI_FUSED, T, L, S, C, P, SP)                                         \
+            else                                                                                   \
+                  LAUNCH_ONE(EPI_PLAIN, T, L, S, C, P, SP)                                         \
+            break;
             STREAM_CONFIGS(X)
 #undef X
+#undef LAUNCH_ONE
       default:
             return fail(-EINVAL, "unknown stream configuration %d", cfg);
       }
@@ -496,12 +431,12 @@ int launch_stream_cfg(int cfg, const CsrArgs &a, const StreamPlan &sp) {
 }
 
 // Configuration of the TMA-staged kernel for one segment.  Measured on B200
-// (profiles/kbench_*.txt): warp-specialised variants win everywhere; rows of
+// (profiles/r1_kbench_*.txt): warp-specialised variants win everywhere; rows of
 // ~16+ entries want several lanes per row (more gathers in flight), short rows
 // want one thread per row and several passes per tile so a tile still carries
 // a few thousand entries.  warps_per_block picks the CTA size within a class.
 int stream_cfg_for(int wpb, double mean_len, bool regular) {
-      if (g_knobs.csr_stream_cfg >= 0 && g_knobs.csr_stream_cfg < kNumStreamCfg)
+      if (g_knobs.csr_stream_cfg >= 0 && stream_shape(g_knobs.csr_stream_cfg))
             return g_knobs.csr_stream_cfg;
       if (!regular) // power-law / ragged: split tiles by entry, not by row (cfg 33: 30 % vs 26 %
                     // for cfg 22 on R-MAT 22, profiles/r1_kbench_rmat22_split_cfgs2.txt)
@@ -513,8 +448,244 @@ int stream_cfg_for(int wpb, double mean_len, bool regular) {
       return wpb <= 2 ? 24 : 26;
 }
 
+int ensure_dot(double **buf, long long *cap, long long n) {
+      if (n <= *cap)
+            return 0;
+      cudaFree(*buf);
+      *buf = nullptr, *cap = 0;
+      B200_CUDA(cudaMalloc(buf, (size_t)n * sizeof(double)));
+      *cap = n;
+      return 0;
+}
+
+} // namespace
+
+// =================================================================== SELL-P
+namespace {
+
+// Gather locality: how much of x does a block of 256 consecutive rows span?  Median over up to
+// 64 sampled blocks, as a fraction of N.  Stencils and banded matrices: ~0; uniform random
+// columns: ~1.
+template <typename Src>
+double measure_gather_span(const Src &src, long long M, long long N) {
+      if (M <= 0 || N <= 0)
+            return 0.0;
+      constexpr int kSamples = 64;
+      constexpr long long kBlock = 256;
+      const int n = (int)std::min<long long>(kSamples, (M + kBlock - 1) / kBlock);
+      const long long stride = std::max<long long>(kBlock, M / n / kBlock * kBlock);
+      int *d_lo = nullptr, *d_hi = nullptr;
+      if (cudaMalloc(&d_lo, n * sizeof(int)) != cudaSuccess ||
+          cudaMalloc(&d_hi, n * sizeof(int)) != cudaSuccess) {
+            cudaFree(d_lo);
+            cudaGetLastError();
+            return 0.0;
+      }
+      col_extent_kernel<<<n, 256>>>(src, M, kBlock, stride, n, d_lo, d_hi);
+      std::vector<int> lo(n), hi(n);
+      cudaMemcpy(lo.data(), d_lo, n * sizeof(int), cudaMemcpyDeviceToHost);
+      cudaMemcpy(hi.data(), d_hi, n * sizeof(int), cudaMemcpyDeviceToHost);
+      cudaFree(d_lo), cudaFree(d_hi);
+      if (cudaGetLastError() != cudaSuccess)
+            return 0.0;
+      std::vector<double> span;
+      for (int i = 0; i < n; ++i)
+            span.push_back(hi[i] >= lo[i] ? (double)(hi[i] - lo[i] + 1) / (double)N : 0.0);
+      std::sort(span.begin(), span.end());
+      return span[span.size() / 2];
+}
+
+int sell_panels_for(long long N, double gather_span) {
+      if (g_knobs.sell_panels > 0)
+            return std::min(64, g_knobs.sell_panels);
+      const double x_mb = (double)N * 8.0 / (1 << 20);
+      // x fits the L2 beside the matrix streams, or the rows only touch a narrow band of it
+      if (x_mb <= 48.0 || gather_span * x_mb <= 24.0)
+            return 1;
+      const int k = (int)((x_mb + g_knobs.sell_panel_mb - 1) / g_knobs.sell_panel_mb);
+      return std::max(1, std::min(64, k));
+}
+
+// Host part of the build: per panel and window, order the rows by their entry count
+// (descending, ties by row index -- a stable counting sort), emit perm and the slice offsets.
+void sell_plan_host(const std::vector<int> &counts, long long M, int K, int sigma,
+                    std::vector<int> &perm, std::vector<long long> &soff, long long *nnz_in,
+                    std::vector<int> *long_rows) {
+      const long long S = (M + 31) / 32;
+      perm.assign((size_t)K * S * 32, -1);
+      std::vector<long long> width((size_t)K * S, 0);
+      const long long n_win = (M + sigma - 1) / sigma;
+      long long nnz_total = 0;
+#pragma omp parallel for schedule(dynamic, 4) reduction(+ : nnz_total) collapse(2)
+      for (int p = 0; p < K; ++p) {
+            for (long long w = 0; w < n_win; ++w) {
+                  const long long r0 = w * sigma, r1 = std::min(M, r0 + sigma);
+                  const int *cnt = counts.data() + (size_t)p * M;
+                  int maxc = 0;
+                  for (long long r = r0; r < r1; ++r)
+                        maxc = std::max(maxc, cnt[r]);
+                  // bucket b holds the rows with count maxc - b; excluded rows (-1) come last
+                  std::vector<int> start((size_t)maxc + 3, 0);
+                  for (long long r = r0; r < r1; ++r)
+                        ++start[(size_t)(cnt[r] < 0 ? maxc + 1 : maxc - cnt[r]) + 1];
+                  for (size_t b = 1; b < start.size(); ++b)
+                        start[b] += start[b - 1];
+                  const long long base = ((long long)p * S + r0 / 32) * 32;
+                  for (long long r = r0; r < r1; ++r) {
+                        const size_t b = (size_t)(cnt[r] < 0 ? maxc + 1 : maxc - cnt[r]);
+                        const int pos = start[b]++;
+                        if (cnt[r] >= 0) {
+                              perm[(size_t)(base + pos)] = (int)r;
+                              nnz_total += cnt[r];
+                        }
+                  }
+                  // slice width = count of its first (longest) row
+                  for (long long s = r0 / 32; s < (r1 + 31) / 32; ++s) {
+                        const int first = perm[(size_t)(((long long)p * S + s) * 32)];
+                        width[(size_t)p * S + s] = first >= 0 ? cnt[first] : 0;
+                  }
+            }
+      }
+      *nnz_in = nnz_total;
+      soff.assign((size_t)K * (S + 1), 0);
+      long long run = 0;
+      for (int p = 0; p < K; ++p) {
+            for (long long s = 0; s < S; ++s) {
+                  soff[(size_t)p * (S + 1) + s] = run;
+                  run += 32 * width[(size_t)p * S + s];
+            }
+            soff[(size_t)p * (S + 1) + S] = run;
+      }
+      if (long_rows) {
+            long_rows->clear();
+            for (long long r = 0; r < M; ++r)
+                  if (counts[r] < 0)
+                        long_rows->push_back((int)r);
+      }
+}
+
+template <typename Src>
+int sell_build(const Src &src, long long M, long long N, int K, int max_row, SellPlan &sp,
+               std::vector<int> *long_rows) {
+      sp.state = -1;
+      if (M <= 0 || M >= (1ll << 31) - 64)
+            return 0;
+      const int sigma = std::max(32, g_knobs.sell_sigma / 32 * 32);
+      const long long S = (M + 31) / 32;
+      PanelBounds pb{};
+      pb.K = K;
+      for (int p = 0; p <= K; ++p)
+            pb.pc[p] = (int)(N * p / K);
+      sp.pc.assign(pb.pc, pb.pc + K + 1);
+
+      int *d_counts = nullptr;
+      B200_CUDA(cudaMalloc(&d_counts, (size_t)K * M * sizeof(int)));
+      sell_count_kernel<<<blocks_for(M, 256), 256>>>(src, M, pb, max_row, d_counts);
+      std::vector<int> counts((size_t)K * M);
+      cudaError_t e = cudaMemcpy(counts.data(), d_counts, counts.size() * sizeof(int),
+                                 cudaMemcpyDeviceToHost);
+      cudaFree(d_counts);
+      if (e != cudaSuccess)
+            return fail(-EIO, "SELL row counts failed: %s", cudaGetErrorString(e));
+      g_counters.launches += 1;
+      g_counters.d2h += (long long)counts.size() * 4;
+
+      std::vector<int> perm;
+      std::vector<long long> soff;
+      sell_plan_host(counts, M, K, sigma, perm, soff, &sp.nnz_in_slices, long_rows);
+      sp.K = K, sp.sigma = sigma, sp.M = M, sp.n_slices = S;
+      sp.slots = soff.back();
+      int rc = upload(&sp.d_perm, perm);
+      rc = rc ? rc : upload(&sp.d_soff, soff);
+      if (rc)
+            return rc;
+      B200_CUDA(cudaMalloc(&sp.d_ja, ((size_t)sp.slots + 32) * sizeof(int)));
+      B200_CUDA(cudaMalloc(&sp.d_as, ((size_t)sp.slots + 32) * sizeof(double)));
+      sell_fill_kernel<<<blocks_for(S * K * 32, 256), 256>>>(src, S, pb, sp.d_soff, sp.d_perm,
+                                                             sp.d_ja, sp.d_as);
+      g_counters.launches += 1;
+      e = cudaDeviceSynchronize();
+      if (e != cudaSuccess)
+            return fail(-EIO, "SELL fill kernel failed: %s", cudaGetErrorString(e));
+      sp.state = 1;
+      return 0;
+}
+
+// y = A x through the panels: panel 0 stores, later panels accumulate (stream order).
+int sell_run(const SellPlan &sp, int wpb, const double *d_x, double *d_y, int epi_mode,
+             const EpiArgs &epi, cudaStream_t st) {
+      const int threads = 32 * wpb;
+      const int grid = blocks_for(sp.n_slices * 32, threads);
+      for (int p = 0; p < sp.K; ++p) {
+            const long long *soff = sp.d_soff + (size_t)p * (sp.n_slices + 1);
+            const int *perm = sp.d_perm + (size_t)p * sp.n_slices * 32;
+            if (p > 0)
+                  sell_kernel<EPI_ACC><<<grid, threads, 0, st>>>(soff, perm, sp.d_ja, sp.d_as,
+                                                                 sp.n_slices, d_x, d_y, epi);
+            else if (epi_mode == EPI_FUSED)
+                  sell_kernel<EPI_FUSED><<<grid, threads, 0, st>>>(soff, perm, sp.d_ja, sp.d_as,
+                                                                   sp.n_slices, d_x, d_y, epi);
+            else
+                  sell_kernel<EPI_PLAIN><<<grid, threads, 0, st>>>(soff, perm, sp.d_ja, sp.d_as,
+                                                                   sp.n_slices, d_x, d_y, epi);
+            ++g_counters.launches;
+      }
+      return 0;
+}
+
+// Should ids 2 / 4 of this CSR go through SELL-P?  (whole-matrix calls on single-segment handles)
+bool csr_wants_sell(spmv_b200_csr *h) {
+      if (g_knobs.sell == 0 || g_knobs.adaptive_direct || h->segs.size() != 1 || h->M < 64)
+            return false;
+      if (g_knobs.sell == 1)
+            return true;
+      const Segment &sg = h->segs[0];
+      if (!sg.regular)
+            return true; // ragged / power-law rows: sorted slices instead of per-bin row lists
+      // regular rows, but x is too large for the L2 and the columns are scattered
+      return sell_panels_for(h->N, h->gather_span) > 1;
+}
+
+int csr_ensure_sell(spmv_b200_csr *h) {
+      if (h->sell.state != 0)
+            return h->sell.state == 1 ? 0 : -1;
+      const int K = sell_panels_for(h->N, h->gather_span);
+      std::vector<int> long_rows;
+      int rc;
+      if (h->wide)
+            rc = sell_build(CsrSrc<long long>{(const long long *)h->d_irp, h->d_ja, h->d_as}, h->M,
+                            h->N, K, g_knobs.sell_max_row, h->sell, &long_rows);
+      else
+            rc = sell_build(CsrSrc<int>{(const int *)h->d_irp, h->d_ja, h->d_as}, h->M, h->N, K,
+                            g_knobs.sell_max_row, h->sell, &long_rows);
+      if (rc || h->sell.state != 1)
+            return -1;
+      // rows too long for a slice: CTA per row up to 65 536 entries, split beyond
+      std::vector<int> blk, spl;
+      for (int r : long_rows)
+            (h->h_irp[r + 1] - h->h_irp[r] <= kKindMax[6] ? blk : spl).push_back(r);
+      h->sell.n_long = (long long)long_rows.size();
+      h->sell.long_block.n = (long long)blk.size();
+      if (upload(&h->sell.long_block.d_rows, blk) || build_split(h, spl, h->sell.long_split)) {
+            free_sell(h->sell);
+            h->sell.state = -1;
+            return -1;
+      }
+      return 0;
+}
+
+} // namespace
+
+// ================================================================== routing
+namespace b200 {
+
+constexpr long long kStreamDotSlots = 32768; // >= CTAs * consumer warps of any stream launch
+
 template <typename OffT>
-int run_kernel(spmv_b200_csr *h, int kernel, int wpb, Segment &sg, const CsrArgs &a) {
+static int run_kernel(spmv_b200_csr *h, int kernel, int wpb, Segment &sg, const CsrArgs &a) {
+      if (a.epi_mode == EPI_FUSED && kernel != SPMV_B200_CSR_ADAPTIVE &&
+          kernel != SPMV_B200_CSR_STREAM)
+            return fail(-ENOTSUP, "the fused epilogue exists for CSR kernels 2 and 4 only");
       switch (kernel) {
       case SPMV_B200_CSR_THREAD_ROW:
             launch_vec<OffT>(a, 0, sg.r0, sg.r1 - sg.r0, nullptr, -1);
@@ -526,8 +697,12 @@ int run_kernel(spmv_b200_csr *h, int kernel, int wpb, Segment &sg, const CsrArgs
             // Adaptive = per segment, the kernel family that measures best for its row-length
             // profile: a regular segment (one length bin holds >= 90 % of the rows) streams
             // through the TMA-staged tile kernel, which also bins its own long rows; an
-            // irregular one goes through the direct binned kernels.
-            if (!sg.regular || g_knobs.adaptive_direct) {
+            // irregular one goes through the direct binned kernels (whole irregular matrices
+            // never get here: csr_run routes them to the sorted slices of SELL-P).
+            if (a.epi_mode != EPI_FUSED && (!sg.regular || g_knobs.adaptive_direct)) {
+                  int rc = build_bin_lists(h, sg);
+                  if (rc)
+                        return rc;
                   run_adaptive<OffT>(a, sg);
                   return 0;
             }
@@ -536,16 +711,21 @@ int run_kernel(spmv_b200_csr *h, int kernel, int wpb, Segment &sg, const CsrArgs
             launch_block_rows<OffT>(a, sg.r0, sg.r1 - sg.r0, nullptr);
             return 0;
       case SPMV_B200_CSR_STREAM: {
-            const double mean_len = sg.r1 > sg.r0 ? (double)(h->h_irp[sg.r1] - h->h_irp[sg.r0]) / (double)(sg.r1 - sg.r0) : 0.0;
+            const double mean_len = sg.r1 > sg.r0 ? (double)(h->h_irp[sg.r1] - h->h_irp[sg.r0]) /
+                                                        (double)(sg.r1 - sg.r0)
+                                                  : 0.0;
             const int cfg = stream_cfg_for(wpb, mean_len, sg.regular);
             StreamPlan &sp = sg.stream[cfg];
             if (!sp.built) {
-                  const StreamShape &s = kStreamShapes[cfg];
+                  const StreamShape &s = *stream_shape(cfg);
                   int rc = build_stream(h, sg, s.threads / s.lpr * s.passes, s.cap, sp);
                   if (rc)
                         return rc;
             }
-            int rc = launch_stream_cfg<OffT>(cfg, a, sp);
+            if (a.epi_mode == EPI_FUSED &&
+                (sp.long_lists[5].n || sp.long_lists[6].n || sp.split.n_rows))
+                  return fail(-ENOTSUP, "fused epilogue: the matrix has rows longer than a stage");
+            int rc = launch_stream_cfg<OffT>(cfg, a, sp, nullptr);
             if (rc)
                   return rc;
             launch_long_lists<OffT>(a, sp.long_lists, sp.split);
@@ -557,82 +737,137 @@ int run_kernel(spmv_b200_csr *h, int kernel, int wpb, Segment &sg, const CsrArgs
 }
 
 int csr_run_segment(spmv_b200_csr *h, Segment &sg, int kernel, int wpb, const double *d_x,
-                    double *d_y, const PushArgs &push, cudaStream_t st) {
-      CsrArgs a{h, d_x, d_y, push, st, 32 * wpb};
+                    double *d_y, int epi_mode, const EpiArgs &epi, cudaStream_t st) {
+      CsrArgs a{h, d_x, d_y, epi_mode, epi, st, 32 * wpb};
       return h->wide ? run_kernel<long long>(h, kernel, wpb, sg, a)
                      : run_kernel<int>(h, kernel, wpb, sg, a);
 }
 
 int csr_run(spmv_b200_csr *h, int kernel, int wpb, long long row0, long long row1,
-            const double *d_x, double *d_y, const PushArgs &push, void *stream) {
+            const double *d_x, double *d_y, int epi_mode, const EpiArgs &epi_in, void *stream) {
       if (!h)
             return fail(-EINVAL, "null CSR handle");
       wpb = clamp_wpb(wpb);
-      bool any = false;
-      for (auto &sg : h->segs) {
-            if (sg.r0 < row0 || sg.r1 > row1)
-                  continue;
-            if (sg.r1 == sg.r0)
-                  continue;
-            any = true;
-            int rc = csr_run_segment(h, sg, kernel, wpb, d_x, d_y, push, as_stream(stream));
-            if (rc)
-                  return rc;
+      cudaStream_t st = as_stream(stream);
+      EpiArgs epi = epi_in;
+      const bool whole = row0 == 0 && row1 == h->M;
+      const bool want_dot = epi_mode == EPI_FUSED && epi.w && epi.dot_partial; // dot_partial = out
+      double *dot_out = epi.dot_partial;
+      long long dot_slots = 0;
+      if (epi_mode == EPI_FUSED) {
+            if (!whole || h->segs.size() > 1)
+                  return fail(-ENOTSUP, "fused epilogue: whole-matrix calls on uncut handles only");
+            epi.dot_partial = nullptr;
       }
-      if (!any && row1 > row0 && h->M > 0)
-            return fail(-EINVAL, "rows [%lld,%lld) do not match the cut points given at creation",
-                        row0, row1);
+
+      const bool sell_kernel_id = kernel == SPMV_B200_CSR_ADAPTIVE || kernel == SPMV_B200_CSR_STREAM;
+      if (sell_kernel_id && whole && epi_mode != EPI_PUSH && csr_wants_sell(h) &&
+          csr_ensure_sell(h) == 0) {
+            const SellPlan &sp = h->sell;
+            if (epi_mode == EPI_FUSED) {
+                  if (sp.K > 1 || sp.n_long)
+                        return fail(-ENOTSUP, "fused epilogue: not available on column panels");
+                  if (want_dot) {
+                        if (ensure_dot(&h->d_dot_partial, &h->dot_cap, sp.n_slices))
+                              return -ENOMEM;
+                        epi.dot_partial = h->d_dot_partial;
+                        dot_slots = sp.n_slices;
+                  }
+            }
+            sell_run(sp, wpb, d_x, d_y, epi_mode, epi, st);
+            CsrArgs a{h, d_x, d_y, EPI_PLAIN, EpiArgs{}, st, 512};
+            if (h->wide)
+                  launch_block_rows<long long>(a, 0, sp.long_block.n, sp.long_block.d_rows);
+            else
+                  launch_block_rows<int>(a, 0, sp.long_block.n, sp.long_block.d_rows);
+            launch_split(a, sp.long_split);
+      } else {
+            if (want_dot) {
+                  if (ensure_dot(&h->d_dot_partial, &h->dot_cap, kStreamDotSlots))
+                        return -ENOMEM;
+                  B200_CUDA(cudaMemsetAsync(h->d_dot_partial, 0, kStreamDotSlots * sizeof(double), st));
+                  epi.dot_partial = h->d_dot_partial;
+                  dot_slots = kStreamDotSlots;
+            }
+            // the requested range must be exactly a run of the segments declared at creation
+            long long covered = 0;
+            for (auto &sg : h->segs) {
+                  if (sg.r0 < row0 || sg.r1 > row1 || sg.r1 == sg.r0)
+                        continue;
+                  covered += sg.r1 - sg.r0;
+            }
+            if (covered != row1 - row0 || row0 < 0 || row1 > h->M)
+                  return fail(-EINVAL,
+                              "rows [%lld,%lld) do not match the cut points given at creation", row0,
+                              row1);
+            for (auto &sg : h->segs) {
+                  if (sg.r0 < row0 || sg.r1 > row1 || sg.r1 == sg.r0)
+                        continue;
+                  int rc = csr_run_segment(h, sg, kernel, wpb, d_x, d_y, epi_mode, epi, st);
+                  if (rc)
+                        return rc;
+            }
+      }
+      if (want_dot) {
+            dot_reduce_kernel<<<1, 1024, 0, st>>>(h->d_dot_partial, dot_slots, dot_out);
+            ++g_counters.launches;
+      }
       cudaError_t e = cudaGetLastError();
       if (e != cudaSuccess)
             return fail(-EIO, "CSR kernel %d launch failed: %s", kernel, cudaGetErrorString(e));
       return 0;
 }
 
-// Row chunks for the host-buffer pipeline.  Usable when the matrix is banded enough that the
-// first half of the rows needs at most ~3/4 of x: then x can be uploaded in column order while
-// earlier chunks already compute and earlier parts of y already travel back.
-constexpr int kPipeChunks = 8; // measured on C2 e2e: 4 -> 186, 8 -> 188, 16 -> 174 GFLOP/s
-
-void build_pipe(spmv_b200_csr *h, const int *host_ja) {
-      h->pipe_state = -1;
-      if (!host_ja || h->col_offset != 0 || h->M < kPipeChunks * 4096 || h->NZ < (1 << 22))
-            return;
-      std::vector<long long> cut(kPipeChunks + 1, 0);
-      for (int c = 1; c < kPipeChunks; ++c) {
-            const long long want = h->NZ / kPipeChunks * c;
-            long long r = std::lower_bound(h->h_irp.begin(), h->h_irp.end(), want) - h->h_irp.begin();
-            r = std::min(h->M, (r + 31) / 32 * 32);
-            cut[c] = std::max(r, cut[c - 1]);
-      }
-      cut[kPipeChunks] = h->M;
-      std::vector<long long> hi(kPipeChunks, 0);
-      long long running = 0;
-      for (int c = 0; c < kPipeChunks; ++c) {
-            const long long k0 = h->h_irp[cut[c]], k1 = h->h_irp[cut[c + 1]];
-            int mx = -1;
-#pragma omp parallel for reduction(max : mx) schedule(static)
-            for (long long k = k0; k < k1; ++k)
-                  mx = host_ja[k] > mx ? host_ja[k] : mx;
-            running = std::max(running, (long long)mx + 1);
-            hi[c] = running;
-      }
-      hi[kPipeChunks - 1] = h->N; // whatever is left of x goes up with the last block
-      if (hi[kPipeChunks / 2 - 1] * 4 > h->N * 3)
-            return; // not banded: the first half of the rows already needs (almost) all of x
-      for (int c = 0; c < kPipeChunks; ++c) {
-            Segment sg;
-            sg.r0 = cut[c], sg.r1 = cut[c + 1];
-            if (build_adaptive(h, sg))
-                  return;
-            h->pipe_segs.push_back(sg);
-      }
-      h->pipe_x_hi = hi;
-      h->pipe_state = 1;
+// Largest column referenced by entries [k0, k1): a device reduction (the host-buffer pipeline
+// needs it for matrices that were generated on the device and have no host copy).
+static __global__ void max_col_kernel(const int *__restrict__ ja, long long k0, long long k1,
+                                      int *__restrict__ out) {
+      int mx = -1;
+      for (long long k = k0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; k < k1;
+           k += (long long)gridDim.x * blockDim.x)
+            mx = max(mx, ja[k]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+            mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      if ((threadIdx.x & 31) == 0 && mx >= 0)
+            atomicMax(out, mx);
 }
 
-} // namespace
+static int max_col_range(const int *d_ja, long long k0, long long k1, int *out) {
+      static int *d_out[kMaxDevices] = {nullptr};
+      int dev = 0;
+      cudaGetDevice(&dev);
+      int *&slot = d_out[dev % kMaxDevices];
+      if (!slot)
+            B200_CUDA(cudaMalloc(&slot, sizeof(int)));
+      const int init = -1;
+      B200_CUDA(cudaMemcpy(slot, &init, sizeof(int), cudaMemcpyHostToDevice));
+      if (k1 > k0) {
+            const int grid = (int)std::min<long long>(1184, (k1 - k0 + 255) / 256);
+            max_col_kernel<<<grid, 256>>>(d_ja, k0, k1, slot);
+      }
+      B200_CUDA(cudaMemcpy(out, slot, sizeof(int), cudaMemcpyDeviceToHost));
+      return 0;
+}
+
+int csr_max_col(const spmv_b200_csr *h, long long k0, long long k1, int *out) {
+      return max_col_range(h->d_ja, k0, k1, out);
+}
+int hll_max_col(const spmv_b200_hll *h, long long hack0, long long hack1, int *out) {
+      return max_col_range(h->d_ja, h->h_hoff[hack0], h->h_hoff[hack1], out);
+}
+
+} // namespace b200
 
 // --------------------------------------------------------------- creation --
+static void csr_measure_span(spmv_b200_csr *h) {
+      if (h->wide)
+            h->gather_span = measure_gather_span(
+                CsrSrc<long long>{(const long long *)h->d_irp, h->d_ja, h->d_as}, h->M, h->N);
+      else
+            h->gather_span =
+                measure_gather_span(CsrSrc<int>{(const int *)h->d_irp, h->d_ja, h->d_as}, h->M, h->N);
+}
 
 static spmv_b200_csr *csr_alloc_shell(long long M, long long n_local, long long NZ,
                                       long long col_offset) {
@@ -726,6 +961,7 @@ extern "C" spmv_b200_csr *spmv_b200_csr_create_ex(int64_t M, int64_t n_local, in
             spmv_b200_csr_destroy(h);
             return nullptr;
       }
+      csr_measure_span(h);
       return h;
 }
 
@@ -783,26 +1019,19 @@ extern "C" spmv_b200_csr *spmv_b200_csr_gen_stencil27(int nx, int ny, int nz, in
             spmv_b200_csr_destroy(h);
             return nullptr;
       }
+      csr_measure_span(h);
       return h;
 }
 
 extern "C" void spmv_b200_csr_destroy(spmv_b200_csr *h) {
       if (!h)
             return;
-      std::vector<Segment> *groups[2] = {&h->segs, &h->pipe_segs};
-      for (auto *grp : groups)
-      for (auto &sg : *grp) {
-            for (auto &l : sg.lists)
-                  free_list(l);
-            free_split(sg.split);
-            for (auto &kv : sg.stream) {
-                  cudaFree(kv.second.d_tile_row);
-                  cudaFree(kv.second.d_tile_k);
-                  for (auto &l : kv.second.long_lists)
-                        free_list(l);
-                  free_split(kv.second.split);
-            }
-      }
+      for (auto &sg : h->segs)
+            free_segment(sg);
+      for (auto &sg : h->pipe_segs)
+            free_segment(sg);
+      free_sell(h->sell);
+      cudaFree(h->d_dot_partial);
       cudaFree(h->d_irp);
       cudaFree(h->d_ja);
       cudaFree(h->d_as);
@@ -843,17 +1072,61 @@ extern "C" int spmv_b200_csr_plan_info(const spmv_b200_csr *h, int64_t *out, int
       return 0;
 }
 
+extern "C" int spmv_b200_csr_sell_info(spmv_b200_csr *h, int build, int64_t *out, int n_out) {
+      if (!h || !out)
+            return fail(-EINVAL, "null argument");
+      if (build && h->sell.state == 0 && h->segs.size() == 1)
+            csr_ensure_sell(h);
+      const SellPlan &sp = h->sell;
+      const int64_t v[8] = {sp.state, sp.K, sp.sigma, sp.n_slices, sp.slots, sp.nnz_in_slices,
+                            sp.n_long, (int64_t)(h->gather_span * 1e6)};
+      for (int i = 0; i < n_out && i < 8; ++i)
+            out[i] = v[i];
+      return 0;
+}
+
+// Host half of the SELL-P build on caller-supplied per-panel row counts (no GPU involved):
+// exposed so the ordering / slice-offset rule can be checked without a device.
+extern "C" int spmv_b200_sell_plan(const int *counts, int64_t M, int K, int sigma, int *perm,
+                                   int64_t *soff) {
+      if (!counts || !perm || !soff || M < 0 || K < 1 || K > 64 || sigma < 32 || sigma % 32)
+            return fail(-EINVAL, "sell_plan: bad arguments");
+      std::vector<int> c(counts, counts + (size_t)K * M), pv;
+      std::vector<long long> sv;
+      long long nnz = 0;
+      sell_plan_host(c, M, K, sigma, pv, sv, &nnz, nullptr);
+      std::copy(pv.begin(), pv.end(), perm);
+      std::copy(sv.begin(), sv.end(), soff);
+      return 0;
+}
+
+extern "C" int spmv_b200_csr_sell_download(const spmv_b200_csr *h, int64_t *soff, int *perm, int *JA,
+                                           double *AS) {
+      if (!h || h->sell.state != 1)
+            return fail(-EINVAL, "no SELL-P plan on this handle");
+      const SellPlan &sp = h->sell;
+      if (soff)
+            B200_CUDA(cudaMemcpy(soff, sp.d_soff, (size_t)sp.K * (sp.n_slices + 1) * 8,
+                                 cudaMemcpyDeviceToHost));
+      if (perm)
+            B200_CUDA(cudaMemcpy(perm, sp.d_perm, (size_t)sp.K * sp.n_slices * 32 * 4,
+                                 cudaMemcpyDeviceToHost));
+      if (JA && sp.slots)
+            B200_CUDA(cudaMemcpy(JA, sp.d_ja, (size_t)sp.slots * 4, cudaMemcpyDeviceToHost));
+      if (AS && sp.slots)
+            B200_CUDA(cudaMemcpy(AS, sp.d_as, (size_t)sp.slots * 8, cudaMemcpyDeviceToHost));
+      return 0;
+}
+
 extern "C" int spmv_b200_csr_spmv(spmv_b200_csr *h, int kernel, int wpb, const double *d_x,
                                   double *d_y, void *stream) {
-      PushArgs none{};
-      return csr_run(h, kernel, wpb, 0, h ? h->M : 0, d_x, d_y, none, stream);
+      return csr_run(h, kernel, wpb, 0, h ? h->M : 0, d_x, d_y, EPI_PLAIN, EpiArgs{}, stream);
 }
 
 extern "C" int spmv_b200_csr_spmv_rows(spmv_b200_csr *h, int kernel, int wpb, int64_t row0,
                                        int64_t row1, const double *d_x, double *d_y,
                                        void *stream) {
-      PushArgs none{};
-      return csr_run(h, kernel, wpb, row0, row1, d_x, d_y, none, stream);
+      return csr_run(h, kernel, wpb, row0, row1, d_x, d_y, EPI_PLAIN, EpiArgs{}, stream);
 }
 
 extern "C" int spmv_b200_csr_spmv_rows_push(spmv_b200_csr *h, int kernel, int wpb, int64_t row0,
@@ -863,24 +1136,41 @@ extern "C" int spmv_b200_csr_spmv_rows_push(spmv_b200_csr *h, int kernel, int wp
                                             void *stream) {
       if (n_push < 0 || n_push > 2)
             return fail(-EINVAL, "n_push must be 0..2");
-      PushArgs p{};
-      p.n = n_push;
+      EpiArgs p{};
+      p.n_push = n_push;
       for (int i = 0; i < n_push; ++i) {
             p.row0[i] = push_row0[i];
             p.row1[i] = push_row1[i];
             p.dst[i] = d_push_dst[i];
       }
-      return csr_run(h, kernel, wpb, row0, row1, d_x, d_y, p, stream);
+      return csr_run(h, kernel, wpb, row0, row1, d_x, d_y, n_push ? EPI_PUSH : EPI_PLAIN, p, stream);
+}
+
+extern "C" int spmv_b200_csr_spmv_fused(spmv_b200_csr *h, int kernel, int wpb, const double *d_x,
+                                        double *d_y, double alpha, double beta, const double *d_z,
+                                        const double *d_w, double *d_dot, void *stream) {
+      EpiArgs e{};
+      e.alpha = alpha, e.beta = beta;
+      e.z = d_z;
+      e.w = d_dot ? d_w : nullptr;
+      e.dot_partial = d_dot; // csr_run swaps in the per-warp scratch and reduces into d_dot
+      return csr_run(h, kernel, wpb, 0, h ? h->M : 0, d_x, d_y, EPI_FUSED, e, stream);
 }
 
 extern "C" int spmv_b200_csr_launches(const spmv_b200_csr *h, int kernel) {
       if (!h)
             return -EINVAL;
+      const bool sell_id = kernel == SPMV_B200_CSR_ADAPTIVE || kernel == SPMV_B200_CSR_STREAM;
+      if (sell_id && h->sell.state == 1 && csr_wants_sell(const_cast<spmv_b200_csr *>(h)))
+            return h->sell.K + (h->sell.long_block.n > 0) + (h->sell.long_split.n_rows ? 2 : 0);
       int n = 0;
       for (auto &sg : h->segs) {
             if (sg.r1 == sg.r0)
                   continue;
-            if (kernel == SPMV_B200_CSR_ADAPTIVE && sg.regular && !g_knobs.adaptive_direct) {
+            const bool streamed = kernel == SPMV_B200_CSR_STREAM ||
+                                  (kernel == SPMV_B200_CSR_ADAPTIVE && sg.regular &&
+                                   !g_knobs.adaptive_direct);
+            if (streamed) {
                   n += 1;
                   for (auto &kv : sg.stream) {
                         for (int k = 5; k < 7; ++k)
@@ -894,14 +1184,6 @@ extern "C" int spmv_b200_csr_launches(const spmv_b200_csr *h, int kernel) {
                         if (!(sg.regular && k <= sg.base_kind))
                               n += sg.lists[k].n > 0;
                   n += sg.split.n_rows ? 2 : 0;
-            } else if (kernel == SPMV_B200_CSR_STREAM) {
-                  n += 1;
-                  for (auto &kv : sg.stream) {
-                        for (int k = 5; k < 7; ++k)
-                              n += kv.second.long_lists[k].n > 0;
-                        n += kv.second.split.n_rows ? 2 : 0;
-                        break;
-                  }
             } else {
                   n += 1;
             }
@@ -947,12 +1229,14 @@ int time_launches(F &&run, int warmup, int reps, int flush_l2, double *ms_out, v
       return rc;
 }
 
+} // namespace
+
+namespace b200 {
 double median_of(std::vector<double> v) {
       std::sort(v.begin(), v.end());
       return v[v.size() / 2];
 }
-
-} // namespace
+} // namespace b200
 
 extern "C" int spmv_b200_csr_time(spmv_b200_csr *h, int kernel, int wpb, const double *d_x,
                                   double *d_y, int warmup, int reps, int flush_l2, double *ms_out,
@@ -961,33 +1245,16 @@ extern "C" int spmv_b200_csr_time(spmv_b200_csr *h, int kernel, int wpb, const d
                            warmup, reps, flush_l2, ms_out, stream);
 }
 
-// ================================================================ HLL handle
 
-struct spmv_b200_hll {
-      long long M = 0, N = 0, NZ = 0, n_hacks = 0, slots = 0;
-      int device = 0;
-      long long *d_hoff = nullptr;
-      int *d_ja = nullptr;
-      double *d_as = nullptr;
-      std::vector<long long> h_hoff;
-      struct Tiles {
-            int *d_tile_h = nullptr;
-            int n_tiles = 0;
-            bool built = false;
-      };
-      std::map<int, Tiles> stream;
-};
+// ================================================================ HLL handle
 
 namespace {
 
 #define HLL_STREAM_CONFIGS(X)                                                                      \
       X(0, 4, 2, 4096)                                                                             \
       X(1, 2, 3, 2048)                                                                             \
-      X(2, 8, 2, 8192)                                                                             \
-      X(3, 4, 3, 4096)                                                                             \
-      X(4, 8, 3, 4096)                                                                             \
-      X(5, 4, 4, 2048)
-constexpr int kNumHllStreamCfg = 6;
+      X(2, 8, 2, 8192)
+constexpr int kNumHllStreamCfg = 3;
 struct HllStreamShape {
       int warps, stages, cap;
 };
@@ -1033,44 +1300,100 @@ int hll_alloc(spmv_b200_hll *h, const std::vector<int> &width) {
                            cudaMemcpyHostToDevice));
       B200_CUDA(cudaMalloc(&h->d_ja, ((size_t)h->slots + 32) * sizeof(int)));
       B200_CUDA(cudaMalloc(&h->d_as, ((size_t)h->slots + 32) * sizeof(double)));
+      B200_CUDA(cudaMalloc(&h->d_rowlen, ((size_t)h->n_hacks * 32 + 32) * sizeof(int)));
       return 0;
 }
 
-int hll_run(spmv_b200_hll *h, int kernel, int wpb, const double *d_x, double *d_y,
-            const PushArgs &push, void *stream) {
+HllSrc hll_src(const spmv_b200_hll *h) { return HllSrc{h->d_hoff, h->d_ja, h->d_as, h->d_rowlen}; }
+
+bool hll_wants_sell(spmv_b200_hll *h) {
+      if (g_knobs.sell == 0 || h->M < 64)
+            return false;
+      if (g_knobs.sell == 1)
+            return true;
+      return sell_panels_for(h->N, h->gather_span) > 1;
+}
+
+int hll_ensure_sell(spmv_b200_hll *h) {
+      if (h->sell.state != 0)
+            return h->sell.state == 1 ? 0 : -1;
+      const int K = sell_panels_for(h->N, h->gather_span);
+      int rc = sell_build(hll_src(h), h->M, h->N, K, 0x7fffffff, h->sell, nullptr);
+      return rc || h->sell.state != 1 ? -1 : 0;
+}
+
+} // namespace
+
+namespace b200 {
+
+// Hacks [hack0, hack1) (the stream kernel and the SELL-P route only take the whole matrix).
+int hll_run_range(spmv_b200_hll *h, int kernel, int wpb, long long hack0, long long hack1,
+                  const double *d_x, double *d_y, int epi_mode, const EpiArgs &epi_in,
+                  void *stream) {
       if (!h)
             return fail(-EINVAL, "null HLL handle");
-      if (h->n_hacks == 0)
+      if (h->n_hacks == 0 || hack1 <= hack0)
             return 0;
+      if (hack0 < 0 || hack1 > h->n_hacks)
+            return fail(-EINVAL, "hack range [%lld,%lld) out of bounds", hack0, hack1);
       wpb = clamp_wpb(wpb);
       cudaStream_t st = as_stream(stream);
       const int threads = 32 * wpb;
-      const int grid = blocks_for(h->n_hacks * 32, threads);
+      const long long n = hack1 - hack0;
+      const int grid = blocks_for(n * 32, threads);
+      const bool whole = hack0 == 0 && hack1 == h->n_hacks;
+      EpiArgs epi = epi_in;
+      const bool want_dot = epi_mode == EPI_FUSED && epi.w && epi.dot_partial;
+      double *dot_out = epi.dot_partial;
+      long long dot_slots = 0;
+      if (epi_mode == EPI_FUSED) {
+            if (kernel != SPMV_B200_HLL_WARP_HACK || !whole)
+                  return fail(-ENOTSUP, "the fused epilogue exists for HLL kernel 2, whole matrix");
+            epi.dot_partial = nullptr;
+            if (want_dot) {
+                  if (ensure_dot(&h->d_dot_partial, &h->dot_cap, h->n_hacks))
+                        return -ENOMEM;
+                  epi.dot_partial = h->d_dot_partial;
+                  dot_slots = h->n_hacks;
+            }
+      }
       switch (kernel) {
       case SPMV_B200_HLL_THREAD_ROW_RM:
       case SPMV_B200_HLL_THREAD_ROW:
-            hll_warp_kernel<1, false><<<grid, threads, 0, st>>>(h->d_hoff, h->d_ja, h->d_as,
-                                                                h->n_hacks, h->M, d_x, d_y, push);
+            hll_warp_kernel<1, EPI_PLAIN><<<grid, threads, 0, st>>>(h->d_hoff, h->d_ja, h->d_as, hack0,
+                                                                    hack1, h->M, d_x, d_y, epi);
             break;
       case SPMV_B200_HLL_WARP_HACK: {
-            // Measured (profiles/r1_kbench_c2_sweep.txt, r1_kbench_c3.txt): lane = row with
-            // 64/32-bit loads wins whenever x is cache friendly (C2: 99 % vs 97 % / 88 %); the
-            // 256/128-bit variant wins when x cannot live in L2 (C3, x = 128 MB: 3.8-4.6 ms vs 4.7)
-            int vec = g_knobs.hll_vec;
-            if (vec != 1 && vec != 2 && vec != 4)
-                  vec = h->N * 8 > (96ll << 20) ? 4 : 1;
-            if (vec == 1)
-                  hll_warp_kernel<1, true><<<grid, threads, 0, st>>>(
-                      h->d_hoff, h->d_ja, h->d_as, h->n_hacks, h->M, d_x, d_y, push);
+            // x larger than the L2 and scattered columns: column panels (sell_kernels.cuh); the
+            // slices are built on the GPU from this very HLL
+            if (whole && hll_wants_sell(h) && hll_ensure_sell(h) == 0 &&
+                (epi_mode != EPI_FUSED || h->sell.K == 1)) {
+                  sell_run(h->sell, wpb, d_x, d_y, epi_mode, epi, st);
+                  --g_counters.launches; // counted again below
+                  break;
+            }
+            // Measured (profiles/r1_kbench_c2_sweep.txt): lane = row with 64/32-bit loads wins
+            // whenever the gather is cache friendly (C2: 99 % vs 97 % / 88 % for the 256/128-bit
+            // and 128/64-bit variants, whose lanes share rows and split their gathers); the wide
+            // variants stay selectable with the hll_vec knob.
+            const int vec = g_knobs.hll_vec;
+            if (epi_mode == EPI_FUSED)
+                  hll_warp_kernel<1, EPI_FUSED><<<grid, threads, 0, st>>>(
+                      h->d_hoff, h->d_ja, h->d_as, hack0, hack1, h->M, d_x, d_y, epi);
             else if (vec == 2)
-                  hll_warp_kernel<2, true><<<grid, threads, 0, st>>>(
-                      h->d_hoff, h->d_ja, h->d_as, h->n_hacks, h->M, d_x, d_y, push);
+                  hll_warp_kernel<2, EPI_PLAIN><<<grid, threads, 0, st>>>(
+                      h->d_hoff, h->d_ja, h->d_as, hack0, hack1, h->M, d_x, d_y, epi);
+            else if (vec == 4)
+                  hll_warp_kernel<4, EPI_PLAIN><<<grid, threads, 0, st>>>(
+                      h->d_hoff, h->d_ja, h->d_as, hack0, hack1, h->M, d_x, d_y, epi);
             else
-                  hll_warp_kernel<4, true><<<grid, threads, 0, st>>>(
-                      h->d_hoff, h->d_ja, h->d_as, h->n_hacks, h->M, d_x, d_y, push);
+                  hll_warp_kernel<1, EPI_PLAIN><<<grid, threads, 0, st>>>(
+                      h->d_hoff, h->d_ja, h->d_as, hack0, hack1, h->M, d_x, d_y, epi);
             break;
       }
       case SPMV_B200_HLL_STREAM: {
+            if (!whole)
+                  return fail(-ENOTSUP, "the staged HLL kernel runs on the whole matrix only");
             const int cfg = hll_stream_cfg_for(wpb);
             auto &t = h->stream[cfg];
             if (!t.built) {
@@ -1085,18 +1408,12 @@ int hll_run(spmv_b200_hll *h, int kernel, int wpb, const double *d_x, double *d_
             auto kern = hll_stream_kernel<W, S, C>;                                                \
             constexpr size_t smem = (size_t)S * C * 12 + S * 8 + 16;                               \
             static int occ_by_dev[kMaxDevices] = {0};                                              \
-            int &occ = occ_by_dev[h->device % kMaxDevices];                                        \
-            if (!occ) {                                                                            \
-                  B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                                 (int)smem));                                      \
-                  B200_CUDA(                                                                       \
-                      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, W * 32, smem));    \
-                  if (occ < 1)                                                                     \
-                        return fail(-EINVAL, "HLL stream cfg %d does not fit on an SM", id);       \
-            }                                                                                      \
-            const int g = std::min(t.n_tiles, occ * g_sm_count);                                   \
+            int rc = stream_occupancy(kern, W * 32, smem, h->device, occ_by_dev);                  \
+            if (rc)                                                                                \
+                  return rc;                                                                       \
+            const int g = std::min(t.n_tiles, occ_by_dev[h->device % kMaxDevices] * g_sm_count);   \
             kern<<<g, W * 32, smem, st>>>(h->d_hoff, h->d_ja, h->d_as, t.d_tile_h, t.n_tiles,      \
-                                          h->M, d_x, d_y, push);                                   \
+                                          h->M, d_x, d_y);                                         \
             break;                                                                                 \
       }
                   HLL_STREAM_CONFIGS(X)
@@ -1108,13 +1425,17 @@ int hll_run(spmv_b200_hll *h, int kernel, int wpb, const double *d_x, double *d_
             return fail(-EINVAL, "unknown HLL kernel id %d", kernel);
       }
       ++g_counters.launches;
+      if (want_dot) {
+            dot_reduce_kernel<<<1, 1024, 0, st>>>(h->d_dot_partial, dot_slots, dot_out);
+            ++g_counters.launches;
+      }
       cudaError_t e = cudaGetLastError();
       if (e != cudaSuccess)
             return fail(-EIO, "HLL kernel %d launch failed: %s", kernel, cudaGetErrorString(e));
       return 0;
 }
 
-} // namespace
+} // namespace b200
 
 extern "C" spmv_b200_hll *spmv_b200_hll_create(const sparse_hll *H, int is_col_major) {
       if (ensure_device())
@@ -1171,9 +1492,15 @@ extern "C" spmv_b200_hll *spmv_b200_hll_create(const sparse_hll *H, int is_col_m
                   fail(-EIO, "HLL upload failed: %s", cudaGetErrorString(cudaGetLastError()));
             g_counters.h2d += src_slots * 12;
       }
-      if (ok && h->n_hacks > 0 && h->slots > 0) {
-            hll_fill_from_host_layout_kernel<<<blocks_for(h->n_hacks * 32, 256), 256>>>(
-                d_soff, d_sja, d_sas, is_col_major, h->M, h->n_hacks, h->d_hoff, h->d_ja, h->d_as);
+      if (ok && h->n_hacks > 0) {
+            if (!d_soff) // every hack is empty: the kernel still writes the row lengths
+                  ok = cudaMalloc(&d_soff, src_off.size() * sizeof(long long)) == cudaSuccess &&
+                       cudaMemcpy(d_soff, src_off.data(), src_off.size() * sizeof(long long),
+                                  cudaMemcpyHostToDevice) == cudaSuccess;
+            if (ok)
+                  hll_fill_from_host_layout_kernel<<<blocks_for(h->n_hacks * 32, 256), 256>>>(
+                      d_soff, d_sja, d_sas, is_col_major, h->M, h->n_hacks, h->d_hoff, h->d_ja,
+                      h->d_as, h->d_rowlen);
             ++g_counters.launches;
             cudaError_t e = cudaDeviceSynchronize();
             if (e != cudaSuccess) {
@@ -1187,6 +1514,7 @@ extern "C" spmv_b200_hll *spmv_b200_hll_create(const sparse_hll *H, int is_col_m
             spmv_b200_hll_destroy(h);
             return nullptr;
       }
+      h->gather_span = measure_gather_span(hll_src(h), h->M, h->N);
       return h;
 }
 
@@ -1201,23 +1529,41 @@ extern "C" spmv_b200_hll *spmv_b200_hll_from_csr(const spmv_b200_csr *A) {
       h->device = A->device;
       h->M = A->M, h->N = A->N, h->NZ = A->NZ;
       h->n_hacks = (A->M + kHack - 1) / kHack;
+      // hack widths (longest row of each hack) on the GPU; the host only needs them for the
+      // prefix sum that sizes the buffers
       std::vector<int> width((size_t)h->n_hacks, 0);
-      for (long long r = 0; r < A->M; ++r) {
-            const int len = (int)(A->h_irp[r + 1] - A->h_irp[r]);
-            int &w = width[r / kHack];
-            w = std::max(w, len);
+      bool ok = true;
+      if (h->n_hacks > 0) {
+            int *d_width = nullptr;
+            ok = cudaMalloc(&d_width, (size_t)h->n_hacks * sizeof(int)) == cudaSuccess;
+            if (ok) {
+                  const int grid = blocks_for(h->n_hacks * 32, 256);
+                  if (A->wide)
+                        hll_width_kernel<long long><<<grid, 256>>>((const long long *)A->d_irp, A->M,
+                                                                   h->n_hacks, d_width);
+                  else
+                        hll_width_kernel<int><<<grid, 256>>>((const int *)A->d_irp, A->M,
+                                                             h->n_hacks, d_width);
+                  ++g_counters.launches;
+                  ok = cudaMemcpy(width.data(), d_width, (size_t)h->n_hacks * sizeof(int),
+                                  cudaMemcpyDeviceToHost) == cudaSuccess;
+            }
+            cudaFree(d_width);
+            if (!ok)
+                  fail(-EIO, "hack width kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
       }
-      bool ok = hll_alloc(h, width) == 0;
-      if (ok && h->n_hacks > 0 && h->slots > 0) {
+      ok = ok && hll_alloc(h, width) == 0;
+      if (ok && h->n_hacks > 0) {
             const int grid = blocks_for(h->n_hacks * 32, 256);
             if (A->wide)
                   hll_fill_from_csr_kernel<long long><<<grid, 256>>>(
                       (const long long *)A->d_irp, A->d_ja, A->d_as, A->M, h->n_hacks, h->d_hoff,
-                      h->d_ja, h->d_as);
+                      h->d_ja, h->d_as, h->d_rowlen);
             else
                   hll_fill_from_csr_kernel<int><<<grid, 256>>>((const int *)A->d_irp, A->d_ja,
                                                                A->d_as, A->M, h->n_hacks,
-                                                               h->d_hoff, h->d_ja, h->d_as);
+                                                               h->d_hoff, h->d_ja, h->d_as,
+                                                               h->d_rowlen);
             ++g_counters.launches;
             cudaError_t e = cudaDeviceSynchronize();
             if (e != cudaSuccess) {
@@ -1229,6 +1575,7 @@ extern "C" spmv_b200_hll *spmv_b200_hll_from_csr(const spmv_b200_csr *A) {
             spmv_b200_hll_destroy(h);
             return nullptr;
       }
+      h->gather_span = A->gather_span;
       return h;
 }
 
@@ -1237,9 +1584,12 @@ extern "C" void spmv_b200_hll_destroy(spmv_b200_hll *h) {
             return;
       for (auto &kv : h->stream)
             cudaFree(kv.second.d_tile_h);
+      free_sell(h->sell);
+      cudaFree(h->d_dot_partial);
       cudaFree(h->d_hoff);
       cudaFree(h->d_ja);
       cudaFree(h->d_as);
+      cudaFree(h->d_rowlen);
       delete h;
 }
 
@@ -1264,15 +1614,43 @@ extern "C" int spmv_b200_hll_download(const spmv_b200_hll *h, int64_t *hoff, int
       return 0;
 }
 
+extern "C" int spmv_b200_hll_sell_info(spmv_b200_hll *h, int build, int64_t *out, int n_out) {
+      if (!h || !out)
+            return fail(-EINVAL, "null argument");
+      if (build && h->sell.state == 0)
+            hll_ensure_sell(h);
+      const SellPlan &sp = h->sell;
+      const int64_t v[8] = {sp.state, sp.K, sp.sigma, sp.n_slices, sp.slots, sp.nnz_in_slices,
+                            sp.n_long, (int64_t)(h->gather_span * 1e6)};
+      for (int i = 0; i < n_out && i < 8; ++i)
+            out[i] = v[i];
+      return 0;
+}
+
 extern "C" int spmv_b200_hll_spmv(spmv_b200_hll *h, int kernel, int wpb, const double *d_x,
                                   double *d_y, void *stream) {
-      PushArgs none{};
-      return hll_run(h, kernel, wpb, d_x, d_y, none, stream);
+      return hll_run_range(h, kernel, wpb, 0, h ? h->n_hacks : 0, d_x, d_y, EPI_PLAIN, EpiArgs{},
+                           stream);
+}
+
+extern "C" int spmv_b200_hll_spmv_fused(spmv_b200_hll *h, int kernel, int wpb, const double *d_x,
+                                        double *d_y, double alpha, double beta, const double *d_z,
+                                        const double *d_w, double *d_dot, void *stream) {
+      EpiArgs e{};
+      e.alpha = alpha, e.beta = beta;
+      e.z = d_z;
+      e.w = d_dot ? d_w : nullptr;
+      e.dot_partial = d_dot;
+      return hll_run_range(h, kernel, wpb, 0, h ? h->n_hacks : 0, d_x, d_y, EPI_FUSED, e, stream);
 }
 
 extern "C" int spmv_b200_hll_launches(const spmv_b200_hll *h, int kernel) {
-      (void)kernel;
-      return h && h->n_hacks > 0 ? 1 : 0;
+      if (!h || h->n_hacks <= 0)
+            return 0;
+      if (kernel == SPMV_B200_HLL_WARP_HACK && h->sell.state == 1 &&
+          hll_wants_sell(const_cast<spmv_b200_hll *>(h)))
+            return h->sell.K;
+      return 1;
 }
 
 extern "C" int spmv_b200_hll_time(spmv_b200_hll *h, int kernel, int wpb, const double *d_x,
@@ -1285,7 +1663,7 @@ extern "C" int spmv_b200_hll_time(spmv_b200_hll *h, int kernel, int wpb, const d
 // ===================================================== library / device / mem
 
 extern "C" const char *spmv_b200_last_error(void) { return tls_error(); }
-extern "C" const char *spmv_b200_version(void) { return "spmv-b200 0.1 (sm_100a)"; }
+extern "C" const char *spmv_b200_version(void) { return "spmv-b200 0.2 (sm_100a)"; }
 
 extern "C" int spmv_b200_device_count(void) {
       int n = 0;
@@ -1362,10 +1740,13 @@ extern "C" int spmv_b200_flush_l2(void *stream) {
       int rc = ensure_device();
       if (rc)
             return rc;
-      if (!g_flush_buf)
-            B200_CUDA(cudaMalloc(&g_flush_buf, kFlushBytes));
+      int dev = 0;
+      B200_CUDA(cudaGetDevice(&dev));
+      void *&buf = g_flush_buf[dev % kMaxDevices];
+      if (!buf)
+            B200_CUDA(cudaMalloc(&buf, kFlushBytes));
       static int toggle = 0;
-      B200_CUDA(cudaMemsetAsync(g_flush_buf, ++toggle & 0xff, kFlushBytes, as_stream(stream)));
+      B200_CUDA(cudaMemsetAsync(buf, ++toggle & 0xff, kFlushBytes, as_stream(stream)));
       return 0;
 }
 
@@ -1383,503 +1764,38 @@ extern "C" void spmv_b200_counters(int64_t *launches, int64_t *h2d_bytes, int64_
             *d2h_bytes = g_counters.d2h;
 }
 
-// Experiment knobs (kbench sweeps).  Unknown keys return -EINVAL.
+// Experiment knobs (kbench sweeps, tests).  Unknown keys return -EINVAL.
 extern "C" int spmv_b200_set_knob(const char *key, int value) {
       if (!key)
             return -EINVAL;
-      if (!strcmp(key, "stream_hints"))
-            g_knobs.stream_hints = value;
-      else if (!strcmp(key, "csr_stream_cfg"))
-            g_knobs.csr_stream_cfg = value;
-      else if (!strcmp(key, "hll_vec"))
-            g_knobs.hll_vec = value;
-      else if (!strcmp(key, "hll_stream_cfg"))
-            g_knobs.hll_stream_cfg = value;
-      else if (!strcmp(key, "regular_lpr"))
-            g_knobs.regular_lpr = value;
-      else if (!strcmp(key, "force_wide"))
-            g_knobs.force_wide = value;
-      else if (!strcmp(key, "adaptive_direct"))
-            g_knobs.adaptive_direct = value;
-      else if (!strcmp(key, "pipeline"))
-            g_knobs.pipeline = value;
-      else if (!strcmp(key, "l2_fetch_granularity")) {
+      struct {
+            const char *name;
+            int *slot;
+      } table[] = {{"csr_stream_cfg", &g_knobs.csr_stream_cfg},
+                   {"hll_vec", &g_knobs.hll_vec},
+                   {"hll_stream_cfg", &g_knobs.hll_stream_cfg},
+                   {"regular_lpr", &g_knobs.regular_lpr},
+                   {"force_wide", &g_knobs.force_wide},
+                   {"adaptive_direct", &g_knobs.adaptive_direct},
+                   {"pipeline", &g_knobs.pipeline},
+                   {"pipe_chunks", &g_knobs.pipe_chunks},
+                   {"sell", &g_knobs.sell},
+                   {"sell_panels", &g_knobs.sell_panels},
+                   {"sell_sigma", &g_knobs.sell_sigma},
+                   {"sell_panel_mb", &g_knobs.sell_panel_mb},
+                   {"sell_max_row", &g_knobs.sell_max_row},
+                   {"cache", &g_knobs.cache}};
+      for (auto &t : table)
+            if (!strcmp(key, t.name)) {
+                  *t.slot = value;
+                  return 0;
+            }
+      if (!strcmp(key, "l2_fetch_granularity")) {
             // device-wide hint: bytes fetched from HBM on an L2 miss (32, 64 or 128)
             if (ensure_device())
                   return -ENODEV;
             B200_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value));
-      }
-      else
-            return fail(-EINVAL, "unknown knob %s", key);
-      return 0;
-}
-
-// ------------------------------------------------- cross-GPU step ordering --
-// One process per GPU; every rank owns `flags[world]` and an `epoch` word in
-// its own HBM, mapped into the neighbours through CUDA IPC.  After the
-// boundary-row kernel of a step has pushed its halo rows into the neighbours,
-// signal_kernel bumps the local epoch and stores it into slot [my_rank] of
-// every neighbour's flags; before the next step's boundary rows, wait_kernel
-// spins (bounded) until every neighbour's slot has reached the local epoch.
-// No host round trip, no collective library call, capturable in a CUDA graph.
-namespace {
-
-struct PeerSlots {
-      int n;
-      unsigned long long *slot[8];
-};
-
-__global__ void signal_kernel(unsigned long long *epoch, PeerSlots peers) {
-      if (threadIdx.x != 0 || blockIdx.x != 0)
-            return;
-      const unsigned long long e = *epoch + 1;
-      *epoch = e;
-      __threadfence_system(); // halo rows pushed by earlier kernels are visible first
-      for (int i = 0; i < peers.n; ++i)
-            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peers.slot[i]), "l"(e)
-                         : "memory");
-}
-
-__global__ void wait_kernel(const unsigned long long *epoch, PeerSlots mine,
-                            unsigned long long max_spins, int *error) {
-      if (threadIdx.x != 0 || blockIdx.x != 0)
-            return;
-      if (*(volatile int *)error != 0)
-            return; // a previous wait already gave up: do not stall every later step
-      const unsigned long long want = *epoch;
-      for (int i = 0; i < mine.n; ++i) {
-            unsigned long long spins = 0, v;
-            for (;;) {
-                  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine.slot[i])
-                               : "memory");
-                  if (v >= want)
-                        break;
-                  if (++spins > max_spins) { // never hang the GPU: report and go on
-                        atomicExch(error, 1 + i);
-                        return;
-                  }
-                  // plain polling: __nanosleep() rounds up to a scheduler quantum that is
-                  // longer than a whole SpMV step of the 128^3 slab
-            }
-      }
-}
-
-} // namespace
-
-extern "C" int spmv_b200_signal_peers(void *d_epoch, int n, void *const *d_peer_slots,
-                                      void *stream) {
-      if (n < 0 || n > 8)
-            return fail(-EINVAL, "signal_peers: 0..8 peers");
-      PeerSlots p{};
-      p.n = n;
-      for (int i = 0; i < n; ++i)
-            p.slot[i] = static_cast<unsigned long long *>(d_peer_slots[i]);
-      signal_kernel<<<1, 32, 0, as_stream(stream)>>>(static_cast<unsigned long long *>(d_epoch), p);
-      ++g_counters.launches;
-      B200_CUDA(cudaGetLastError());
-      return 0;
-}
-
-extern "C" int spmv_b200_wait_peers(const void *d_epoch, int n, void *const *d_my_slots,
-                                    uint64_t max_spins, int *d_error, void *stream) {
-      if (n < 0 || n > 8)
-            return fail(-EINVAL, "wait_peers: 0..8 peers");
-      PeerSlots p{};
-      p.n = n;
-      for (int i = 0; i < n; ++i)
-            p.slot[i] = static_cast<unsigned long long *>(d_my_slots[i]);
-      wait_kernel<<<1, 32, 0, as_stream(stream)>>>(static_cast<const unsigned long long *>(d_epoch),
-                                                   p, max_spins, d_error);
-      ++g_counters.launches;
-      B200_CUDA(cudaGetLastError());
-      return 0;
-}
-
-// ------------------------------------------------------------------- IPC --
-extern "C" int spmv_b200_ipc_export(void *d_ptr, unsigned char *handle64) {
-      static_assert(sizeof(cudaIpcMemHandle_t) == SPMV_B200_IPC_HANDLE_BYTES, "handle size");
-      cudaIpcMemHandle_t hd;
-      B200_CUDA(cudaIpcGetMemHandle(&hd, d_ptr));
-      memcpy(handle64, &hd, sizeof hd);
-      return 0;
-}
-extern "C" int spmv_b200_ipc_open(const unsigned char *handle64, void **d_ptr_out) {
-      cudaIpcMemHandle_t hd;
-      memcpy(&hd, handle64, sizeof hd);
-      B200_CUDA(cudaIpcOpenMemHandle(d_ptr_out, hd, cudaIpcMemLazyEnablePeerAccess));
-      return 0;
-}
-extern "C" int spmv_b200_ipc_close(void *d_ptr) {
-      B200_CUDA(cudaIpcCloseMemHandle(d_ptr));
-      return 0;
-}
-extern "C" int spmv_b200_enable_peer(int peer_device) {
-      cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
-      if (e == cudaErrorPeerAccessAlreadyEnabled) {
-            cudaGetLastError();
             return 0;
       }
-      B200_CUDA(e);
-      return 0;
-}
-
-// ================================================================== timer
-// C-linkage stopwatch (reference: include/cuda_timer.cuh, src/cuda_timer.cu).
-
-extern "C" int timer_init(cuda_timer *t) {
-      if (!t || ensure_device())
-            return -1;
-      cudaEvent_t a, b;
-      if (cudaEventCreate(&a) != cudaSuccess)
-            return -1;
-      if (cudaEventCreate(&b) != cudaSuccess) {
-            cudaEventDestroy(a);
-            return -1;
-      }
-      t->start = a, t->stop = b;
-      return 0;
-}
-extern "C" void timer_start(cuda_timer *t, void *stream) {
-      cudaEventRecord((cudaEvent_t)t->start, as_stream(stream));
-}
-extern "C" double timer_stop(cuda_timer *t, void *stream) {
-      float ms = 0.f;
-      if (cudaEventRecord((cudaEvent_t)t->stop, as_stream(stream)) != cudaSuccess ||
-          cudaEventSynchronize((cudaEvent_t)t->stop) != cudaSuccess ||
-          cudaEventElapsedTime(&ms, (cudaEvent_t)t->start, (cudaEvent_t)t->stop) != cudaSuccess) {
-            fail(-EIO, "timer_stop: %s", cudaGetErrorString(cudaGetLastError()));
-            return -1.0;
-      }
-      return (double)ms;
-}
-extern "C" void timer_destroy(cuda_timer *t) {
-      if (!t)
-            return;
-      cudaEventDestroy((cudaEvent_t)t->start);
-      cudaEventDestroy((cudaEvent_t)t->stop);
-      t->start = t->stop = nullptr;
-}
-
-// ============================================ reference-style entry points
-// Host pointers in, host y out, kernel milliseconds returned.  The matrix is
-// uploaded on first sight and kept resident (the reference driver calls 15
-// CSR and 12 HLL variants on the same matrix, src/main.c:271-353).
-
-namespace {
-
-uint64_t fingerprint(const void *p, size_t bytes) {
-      // cheap content check: up to 4096 sampled 8-byte words + the length
-      const unsigned char *b = static_cast<const unsigned char *>(p);
-      uint64_t hsh = 0x9E3779B97F4A7C15ull ^ bytes;
-      const size_t words = bytes / 8;
-      const size_t step = words > 4096 ? words / 4096 : 1;
-      for (size_t w = 0; w < words; w += step) {
-            uint64_t v;
-            memcpy(&v, b + w * 8, 8);
-            hsh = (hsh ^ v) * 0xBF58476D1CE4E5B9ull;
-            hsh ^= hsh >> 29;
-      }
-      return hsh;
-}
-
-struct CsrEntry {
-      const void *A, *irp, *ja, *as;
-      int M, N, NZ;
-      uint64_t fp;
-      spmv_b200_csr *h;
-};
-struct HllEntry {
-      const void *H, *blocks;
-      int M, N, NZ, col_major;
-      uint64_t fp;
-      spmv_b200_hll *h;
-};
-
-std::mutex g_cache_mu;
-std::vector<CsrEntry> g_csr_cache;
-std::vector<HllEntry> g_hll_cache;
-double *g_dx = nullptr, *g_dy = nullptr;
-size_t g_dx_cap = 0, g_dy_cap = 0;
-constexpr size_t kCacheSlots = 4;
-
-uint64_t csr_fp(const sparse_csr *A) {
-      return fingerprint(A->IRP, ((size_t)A->M + 1) * 4) ^
-             (fingerprint(A->JA, (size_t)A->NZ * 4) * 3) ^
-             (fingerprint(A->AS, (size_t)A->NZ * 8) * 5);
-}
-
-spmv_b200_csr *cached_csr(const sparse_csr *A) {
-      const uint64_t fp = csr_fp(A);
-      for (auto &e : g_csr_cache)
-            if (e.A == A && e.irp == A->IRP && e.ja == A->JA && e.as == A->AS && e.M == A->M &&
-                e.N == A->N && e.NZ == A->NZ && e.fp == fp)
-                  return e.h;
-      spmv_b200_csr *h = spmv_b200_csr_create(A);
-      if (!h)
-            return nullptr;
-      if (g_csr_cache.size() >= kCacheSlots) {
-            spmv_b200_csr_destroy(g_csr_cache.front().h);
-            g_csr_cache.erase(g_csr_cache.begin());
-      }
-      g_csr_cache.push_back({A, A->IRP, A->JA, A->AS, A->M, A->N, A->NZ, fp, h});
-      return h;
-}
-
-uint64_t hll_fp(const sparse_hll *H) {
-      uint64_t f = fingerprint(H->blocks, (size_t)H->num_blocks * sizeof(ellpack_block));
-      const int nb = H->num_blocks;
-      const int probes[3] = {0, nb / 2, nb - 1};
-      for (int i = 0; i < 3 && nb > 0; ++i) {
-            const ellpack_block &b = H->blocks[probes[i]];
-            const size_t n = (size_t)b.M * b.max_NZ;
-            f ^= fingerprint(b.JA, n * 4) * (7 + i) ^ fingerprint(b.AS, n * 8) * (11 + i);
-      }
-      return f;
-}
-
-spmv_b200_hll *cached_hll(const sparse_hll *H, int col_major) {
-      const uint64_t fp = hll_fp(H);
-      for (auto &e : g_hll_cache)
-            if (e.H == H && e.blocks == H->blocks && e.M == H->M && e.N == H->N && e.NZ == H->NZ &&
-                e.col_major == col_major && e.fp == fp)
-                  return e.h;
-      spmv_b200_hll *h = spmv_b200_hll_create(H, col_major);
-      if (!h)
-            return nullptr;
-      if (g_hll_cache.size() >= kCacheSlots) {
-            spmv_b200_hll_destroy(g_hll_cache.front().h);
-            g_hll_cache.erase(g_hll_cache.begin());
-      }
-      g_hll_cache.push_back({H, H->blocks, H->M, H->N, H->NZ, col_major, fp, h});
-      return h;
-}
-
-int ensure_vectors(size_t n_x, size_t n_y) {
-      if (n_x > g_dx_cap) {
-            cudaFree(g_dx);
-            g_dx = nullptr, g_dx_cap = 0;
-            B200_CUDA(cudaMalloc(&g_dx, (n_x + 32) * sizeof(double)));
-            g_dx_cap = n_x;
-      }
-      if (n_y > g_dy_cap) {
-            cudaFree(g_dy);
-            g_dy = nullptr, g_dy_cap = 0;
-            B200_CUDA(cudaMalloc(&g_dy, (n_y + 32) * sizeof(double)));
-            g_dy_cap = n_y;
-      }
-      return 0;
-}
-
-template <typename Run>
-double entry_common(long long M, long long N, const double *x, double *y, Run &&timed) {
-      if (!x || !y) {
-            fail(-EINVAL, "null x or y");
-            return -1.0;
-      }
-      if (ensure_vectors((size_t)N, (size_t)M))
-            return -1.0;
-      if (N && cudaMemcpy(g_dx, x, (size_t)N * sizeof(double), cudaMemcpyHostToDevice) !=
-                   cudaSuccess) {
-            fail(-EIO, "x upload failed: %s", cudaGetErrorString(cudaGetLastError()));
-            return -1.0;
-      }
-      g_counters.h2d += N * 8;
-      std::vector<double> ms((size_t)std::max(1, g_knobs.reps));
-      if (timed(ms.data()))
-            return -1.0;
-      if (M && cudaMemcpy(y, g_dy, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost) !=
-                   cudaSuccess) {
-            fail(-EIO, "y download failed: %s", cudaGetErrorString(cudaGetLastError()));
-            return -1.0;
-      }
-      g_counters.d2h += M * 8;
-      const double med = median_of(ms);
-      // an empty matrix launches nothing; report the timer resolution
-      return med > 0.0 ? med : 1e-6;
-}
-
-// Is this host pointer page-locked (cudaHostAlloc / cudaHostRegister)?  Only then do async
-// copies overlap with kernels and with each other.
-bool is_pinned(const void *p) {
-      cudaPointerAttributes at{};
-      if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
-            cudaGetLastError();
-            return false;
-      }
-      return at.type == cudaMemoryTypeHost;
-}
-
-// Host-buffer pipeline for banded matrices (pinned x and y): x goes up in column order on one
-// stream, row chunk c starts as soon as the columns it references have arrived, and its slice
-// of y travels back on a third stream while later chunks compute -- PCIe is used in both
-// directions at once instead of x-up, compute, y-down in sequence.  Returns the time from the
-// first chunk's start to the last chunk's end on the compute stream (ms), or <= 0 on error.
-double csr_pipeline_pass(spmv_b200_csr *h, int kernel, int wpb, const double *x, double *y) {
-      static cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
-      static cudaEvent_t ev_in[kPipeChunks], ev_k[kPipeChunks], t0, t1;
-      if (!s_in) {
-            if (cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking) != cudaSuccess ||
-                cudaStreamCreateWithFlags(&s_cmp, cudaStreamNonBlocking) != cudaSuccess ||
-                cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking) != cudaSuccess) {
-                  fail(-EIO, "pipeline streams: %s", cudaGetErrorString(cudaGetLastError()));
-                  s_in = nullptr;
-                  return -1.0;
-            }
-            for (int c = 0; c < kPipeChunks; ++c) {
-                  cudaEventCreateWithFlags(&ev_in[c], cudaEventDisableTiming);
-                  cudaEventCreateWithFlags(&ev_k[c], cudaEventDisableTiming);
-            }
-            cudaEventCreate(&t0);
-            cudaEventCreate(&t1);
-      }
-      PushArgs none{};
-      long long lo = 0;
-      for (int c = 0; c < kPipeChunks; ++c) {
-            const long long hi = h->pipe_x_hi[c];
-            if (hi > lo)
-                  cudaMemcpyAsync(g_dx + lo, x + lo, (size_t)(hi - lo) * 8, cudaMemcpyHostToDevice,
-                                  s_in);
-            cudaEventRecord(ev_in[c], s_in);
-            lo = std::max(lo, hi);
-      }
-      int rc = 0;
-      for (int c = 0; c < kPipeChunks && !rc; ++c) {
-            Segment &sg = h->pipe_segs[c];
-            cudaStreamWaitEvent(s_cmp, ev_in[c], 0);
-            if (c == 0)
-                  cudaEventRecord(t0, s_cmp);
-            if (sg.r1 > sg.r0)
-                  rc = csr_run_segment(h, sg, kernel, wpb, g_dx, g_dy, none, s_cmp);
-            cudaEventRecord(ev_k[c], s_cmp);
-            cudaStreamWaitEvent(s_out, ev_k[c], 0);
-            if (sg.r1 > sg.r0)
-                  cudaMemcpyAsync(y + sg.r0, g_dy + sg.r0, (size_t)(sg.r1 - sg.r0) * 8,
-                                  cudaMemcpyDeviceToHost, s_out);
-      }
-      cudaEventRecord(t1, s_cmp);
-      cudaError_t e1 = cudaStreamSynchronize(s_cmp), e2 = cudaStreamSynchronize(s_out),
-                  e3 = cudaStreamSynchronize(s_in);
-      if (rc)
-            return -1.0;
-      if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
-            fail(-EIO, "pipelined SpMV failed: %s", cudaGetErrorString(cudaGetLastError()));
-            return -1.0;
-      }
-      g_counters.h2d += h->N * 8;
-      g_counters.d2h += h->M * 8;
-      float ms = 0.f;
-      cudaEventElapsedTime(&ms, t0, t1);
-      return ms > 0.f ? (double)ms : 1e-6;
-}
-
-double csr_entry(const sparse_csr *A, const double *x, double *y, int kernel) {
-      if (!A) {
-            fail(-EINVAL, "null sparse_csr");
-            return -1.0;
-      }
-      if (ensure_device())
-            return -1.0;
-      std::lock_guard<std::mutex> lk(g_cache_mu);
-      spmv_b200_csr *h = cached_csr(A);
-      if (!h)
-            return -1.0;
-      const int wpb = clamp_wpb(t_csr_wpb);
-
-      // banded matrix + page-locked buffers + a kernel that can run on row chunks: pipeline
-      const bool chunkable = kernel == SPMV_B200_CSR_ADAPTIVE || kernel == SPMV_B200_CSR_STREAM;
-      if (g_knobs.pipeline && chunkable && x && y) {
-            if (h->pipe_state == 0)
-                  build_pipe(h, A->JA);
-            if (h->pipe_state == 1 && is_pinned(x) && is_pinned(y) &&
-                ensure_vectors((size_t)A->N, (size_t)A->M) == 0) {
-                  const double pass_ms = csr_pipeline_pass(h, kernel, wpb, x, y);
-                  if (pass_ms <= 0.0)
-                        return -1.0;
-                  if (g_knobs.reps <= 0)
-                        return pass_ms; // y is already home; no separately timed launches wanted
-                  std::vector<double> ms((size_t)g_knobs.reps);
-                  if (spmv_b200_csr_time(h, kernel, wpb, g_dx, g_dy, 0, g_knobs.reps, 0, ms.data(),
-                                         nullptr))
-                        return -1.0;
-                  return median_of(ms);
-            }
-      }
-      return entry_common(A->M, A->N, x, y, [&](double *ms) {
-            return spmv_b200_csr_time(h, kernel, wpb, g_dx, g_dy, g_knobs.warmup,
-                                      std::max(1, g_knobs.reps), 0, ms, nullptr);
-      });
-}
-
-double hll_entry(const sparse_hll *H, const double *x, double *y, int kernel, int col_major) {
-      if (!H) {
-            fail(-EINVAL, "null sparse_hll");
-            return -1.0;
-      }
-      if (ensure_device())
-            return -1.0;
-      std::lock_guard<std::mutex> lk(g_cache_mu);
-      spmv_b200_hll *h = cached_hll(H, col_major);
-      if (!h)
-            return -1.0;
-      const int wpb = t_hll_wpb;
-      return entry_common(H->M, H->N, x, y, [&](double *ms) {
-            return spmv_b200_hll_time(h, kernel, wpb, g_dx, g_dy, g_knobs.warmup,
-                                      std::max(1, g_knobs.reps), 0, ms, nullptr);
-      });
-}
-
-} // namespace
-
-extern "C" void spmv_b200_release_all(void) {
-      std::lock_guard<std::mutex> lk(g_cache_mu);
-      for (auto &e : g_csr_cache)
-            spmv_b200_csr_destroy(e.h);
-      for (auto &e : g_hll_cache)
-            spmv_b200_hll_destroy(e.h);
-      g_csr_cache.clear();
-      g_hll_cache.clear();
-      cudaFree(g_dx), cudaFree(g_dy);
-      g_dx = g_dy = nullptr;
-      g_dx_cap = g_dy_cap = 0;
-}
-
-extern "C" void set_csr_warps_per_block(int wppb) { t_csr_wpb = wppb; }
-extern "C" void set_hll_warps_per_block(int wppb) { t_hll_wpb = wppb; }
-
-extern "C" double csr_spmv_cuda_thread_row(const sparse_csr *A, const double *x, double *y,
-                                           void *) {
-      return csr_entry(A, x, y, SPMV_B200_CSR_THREAD_ROW);
-}
-extern "C" double csr_spmv_cuda_warp_row(const sparse_csr *A, const double *x, double *y,
-                                         void *) {
-      return csr_entry(A, x, y, SPMV_B200_CSR_WARP_ROW);
-}
-extern "C" double csr_spmv_cuda_halfwarp_row(const sparse_csr *A, const double *x, double *y,
-                                             void *) {
-      return csr_entry(A, x, y, SPMV_B200_CSR_ADAPTIVE);
-}
-extern "C" double csr_spmv_cuda_block_row(const sparse_csr *A, const double *x, double *y,
-                                          void *) {
-      return csr_entry(A, x, y, SPMV_B200_CSR_BLOCK_ROW);
-}
-extern "C" double csr_spmv_cuda_halfwarp_row_text(const sparse_csr *A, const double *x, double *y,
-                                                  void *) {
-      return csr_entry(A, x, y, SPMV_B200_CSR_STREAM);
-}
-
-extern "C" double hll_spmv_cuda_threads_row_major(const sparse_hll *H, const double *x, double *y,
-                                                  void *) {
-      return hll_entry(H, x, y, SPMV_B200_HLL_THREAD_ROW_RM, /*col_major=*/0);
-}
-extern "C" double hll_spmv_cuda_threads_col_major(const sparse_hll *H, const double *x, double *y,
-                                                  void *) {
-      return hll_entry(H, x, y, SPMV_B200_HLL_THREAD_ROW, /*col_major=*/1);
-}
-extern "C" double hll_spmv_cuda_warp_block(const sparse_hll *H, const double *x, double *y,
-                                           void *) {
-      return hll_entry(H, x, y, SPMV_B200_HLL_WARP_HACK, /*col_major=*/1);
-}
-extern "C" double hll_spmv_cuda_halfwarp_row(const sparse_hll *H, const double *x, double *y,
-                                             void *) {
-      return hll_entry(H, x, y, SPMV_B200_HLL_STREAM, /*col_major=*/0);
+      return fail(-EINVAL, "unknown knob %s", key);
 }

@@ -78,6 +78,31 @@ class devinfo(C.Structure):
     ]
 
 
+MAX_RANKS = 16
+DIST_BLOB_BYTES = 512
+DIST_AUTO, DIST_PUSH, DIST_NCCL = 0, 1, 2
+
+
+class shard_desc(C.Structure):
+    """spmv_b200_shard_desc (include/spmv_b200.h)."""
+    _fields_ = [(n, C.c_int64) for n in ("r0", "r1", "c0", "c1", "read_lo", "read_hi")]
+
+
+class xfer(C.Structure):
+    _fields_ = [("peer", C.c_int), ("g0", C.c_int64), ("g1", C.c_int64)]
+
+
+class dist_plan(C.Structure):
+    """spmv_b200_dist_plan (include/spmv_b200.h)."""
+    _fields_ = [
+        ("rank", C.c_int), ("world", C.c_int), ("mode", C.c_int), ("all_gather", C.c_int),
+        ("covered", C.c_int), ("n_send", C.c_int), ("n_recv", C.c_int), ("n_cuts", C.c_int),
+        ("boundary_lo", C.c_int64), ("boundary_hi", C.c_int64),
+        ("cuts", C.c_int64 * 2), ("halo_bytes", C.c_int64),
+        ("send", xfer * MAX_RANKS), ("recv", xfer * MAX_RANKS),
+    ]
+
+
 def is_err_ptr(addr):
     """IS_ERR() of include/err.h on an integer address."""
     return addr is not None and addr > (1 << 64) - 4096

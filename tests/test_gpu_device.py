@@ -202,3 +202,215 @@ def test_shard_with_column_offset_from_host_arrays(sp, O, torch):
             ok, worst = O.check_tolerance(y.cpu().numpy(), y_full[r0:r1], bound[r0:r1], TOL)
             assert ok, (wide, kernel, worst)
         h.close()
+
+
+# ----------------------------------------------------------------- SELL-P ------
+def _sell_case(sp, name):
+    if name == "ragged":
+        return sp.gen_ragged(5000, 300)
+    if name == "rmat":
+        return sp.gen_rmat(13, 16)
+    if name == "uniform":
+        return sp.gen_uniform_random(20000, 32)
+    return sp.gen_stencil27(20, 18, 11)
+
+
+@pytest.mark.parametrize("name", ["ragged", "rmat", "uniform", "stencil"])
+def test_sell_layout_bit_exact_and_parity(sp, O, torch, name):
+    """Column-panelled, window-sorted slices (csrc/sell_kernels.cuh): what sits in HBM equals the
+    oracle's independent restatement of the layout rule, for several panel counts / windows /
+    long-row thresholds, from the CSR source; y is within the north-star tolerance from both the
+    CSR and the HLL source."""
+    A = _sell_case(sp, name)
+    IRP, JA, AS = A.IRP.copy(), A.JA.copy(), A.AS.copy()
+    x = np.random.default_rng(5).uniform(-1, 1, A.N)
+    y_ref = O.csr_spmv(A.M, IRP, JA, AS, x)
+    bound = O.csr_abs_bound(A.M, IRP, JA, AS, x)
+    xd = dev(torch, x)
+    y = torch.zeros(A.M, dtype=torch.float64, device="cuda")
+    try:
+        sp.set_knob("sell", 1)
+        for K, sigma, max_row in ((1, 64, 4096), (3, 256, 100), (4, 16384, 4096), (7, 32, 40)):
+            sp.set_knob("sell_panels", K)
+            sp.set_knob("sell_sigma", sigma)
+            sp.set_knob("sell_max_row", max_row)
+            h = sp.CsrDevice.from_host(A)
+            info = h.sell_info(build=True)
+            assert info["state"] == 1 and info["panels"] == K and info["sigma"] == sigma
+            if A.M <= 6000:        # the numpy restatement is a per-row Python loop
+                soff, perm, ja, as_ = h.sell_download()
+                w_soff, w_perm, w_ja, w_as = O.sellp_layout(A.M, A.N, IRP, JA, AS, K, sigma, max_row)
+                assert np.array_equal(soff, w_soff)
+                assert np.array_equal(perm, w_perm)
+                assert np.array_equal(ja, w_ja)
+                assert np.array_equal(as_.view(np.uint64), w_as.view(np.uint64))
+            assert info["long_rows"] == int((np.diff(IRP) > max_row).sum())
+            for kernel in (2, 4):
+                for wpb in (2, 8):
+                    y.fill_(float("nan"))
+                    h.spmv(xd, y, kernel=kernel, warps_per_block=wpb)
+                    ok, worst = O.check_tolerance(y.cpu().numpy(), y_ref, bound, TOL)
+                    assert ok, (name, "csr", K, sigma, max_row, kernel, wpb, worst)
+            assert h.launches(2) >= K
+            if max_row == 4096:
+                hh = h.to_hll()
+                y.fill_(float("nan"))
+                hh.spmv(xd, y, kernel=2, warps_per_block=4)
+                assert hh.sell_info()["state"] == 1 and hh.sell_info()["panels"] == K
+                ok, worst = O.check_tolerance(y.cpu().numpy(), y_ref, bound, TOL)
+                assert ok, (name, "hll", K, sigma, worst)
+                hh.close()
+            h.close()
+    finally:
+        for k, v in (("sell", -1), ("sell_panels", 0), ("sell_sigma", 16384), ("sell_max_row", 4096)):
+            sp.set_knob(k, v)
+
+
+def test_sell_auto_routing(sp, O, torch):
+    """Who goes through SELL-P without a knob: ragged / power-law CSR (one panel while x fits
+    the L2); regular rows stay on the staged kernel; and the host half of the plan (row order and
+    slice offsets) is a pure function of the per-panel row counts."""
+    R = sp.CsrDevice.from_host(sp.gen_rmat(14, 16))
+    S = sp.CsrDevice.from_host(sp.gen_stencil27(24, 24, 24))
+    x = torch.ones(R.N, dtype=torch.float64, device="cuda")
+    y = torch.zeros(R.M, dtype=torch.float64, device="cuda")
+    R.spmv(x, y, kernel=2)
+    assert R.sell_info()["state"] == 1 and R.sell_info()["panels"] == 1
+    xs = torch.ones(S.N, dtype=torch.float64, device="cuda")
+    ys = torch.zeros(S.M, dtype=torch.float64, device="cuda")
+    S.spmv(xs, ys, kernel=2)
+    assert S.sell_info()["state"] == 0
+    assert S.sell_info()["gather_span_ppm"] < 300000 and R.sell_info()["gather_span_ppm"] > 500000
+    R.close()
+    S.close()
+
+
+# ------------------------------------------------------- fused iteration step ------
+@pytest.mark.parametrize("name", ["stencil", "poisson", "rmat_sell"])
+def test_fused_axpby_dot(sp, O, torch, name):
+    """y = alpha A x + beta z and dot = sum y*w in ONE pass over the matrix
+    (spmv_b200_{csr,hll}_spmv_fused): equals the unfused sequence, and the dot product is
+    bit-reproducible from run to run (fixed reduction order)."""
+    A = {"stencil": lambda: sp.gen_stencil27(30, 28, 26), "poisson": lambda: sp.gen_poisson2d(300, 200),
+         "rmat_sell": lambda: sp.gen_rmat(13, 8)}[name]()
+    rng = np.random.default_rng(6)
+    x, z, w = (rng.uniform(-1, 1, n) for n in (A.N, A.M, A.M))
+    alpha, beta = 0.75, -1.25
+    IRP, JA, AS = A.IRP.copy(), A.JA.copy(), A.AS.copy()
+    ax = O.csr_spmv(A.M, IRP, JA, AS, x)
+    bound = O.csr_abs_bound(A.M, IRP, JA, AS, x)
+    want = alpha * ax + beta * z
+    lim = abs(alpha) * bound + abs(beta * z) * 4 * np.finfo(float).eps / 1e-12
+    try:
+        if name == "rmat_sell":
+            sp.set_knob("sell_max_row", 1 << 20)     # no long-row side kernels: fused is allowed
+        h = sp.CsrDevice.from_host(A)
+        handles = [("csr", h, (2, 4))]
+        if name != "rmat_sell":
+            handles.append(("hll", h.to_hll(), (2,)))
+        xd, zd, wd = dev(torch, x), dev(torch, z), dev(torch, w)
+        for fmt, hd, kernels in handles:
+            for kernel in kernels:
+                y = torch.full((A.M,), float("nan"), dtype=torch.float64, device="cuda")
+                dot = torch.zeros(1, dtype=torch.float64, device="cuda")
+                hd.spmv_fused(xd, y, alpha, beta, zd, wd, dot, kernel=kernel)
+                yh = y.cpu().numpy()
+                ok, worst = O.check_tolerance(yh, want, lim, TOL)
+                assert ok, (fmt, kernel, worst)
+                d0 = float(dot.item())
+                assert abs(d0 - float(yh @ w)) <= 1e-10 * float(np.abs(yh * w).sum())
+                hd.spmv_fused(xd, y, alpha, beta, zd, wd, dot, kernel=kernel)
+                assert float(dot.item()) == d0                       # bit-reproducible
+                # ||y||^2 with w = y, no z
+                hd.spmv_fused(xd, y, 1.0, 0.0, None, y, dot, kernel=kernel)
+                yh = y.cpu().numpy()
+                assert abs(float(dot.item()) - float(yh @ yh)) <= 1e-10 * float(yh @ yh)
+                ok, worst = O.check_tolerance(yh, ax, bound, TOL)
+                assert ok, (fmt, kernel, "plain", worst)
+        for _, hd, _ in handles:
+            hd.close()
+    finally:
+        sp.set_knob("sell_max_row", 4096)
+
+
+def test_handle_host_spmv(sp, O, torch):
+    """spmv_b200_{csr,hll}_spmv_host on resident handles, including a generated-in-HBM stencil
+    (no host copy of the matrix: the chunk plan comes from device reductions), pinned and
+    pageable buffers."""
+    nx, ny, nz = 48, 48, 64
+    h = sp.CsrDevice.stencil27(nx, ny, nz)
+    hh = h.to_hll()
+    A = sp.gen_stencil27(nx, ny, nz)
+    x = np.random.default_rng(7).uniform(-1, 1, A.N)
+    y_ref = O.csr_spmv(A.M, A.IRP, A.JA, A.AS, x)
+    bound = O.csr_abs_bound(A.M, A.IRP, A.JA, A.AS, x)
+    xp, yp = sp.pinned_empty(A.N), sp.pinned_empty(A.M)
+    xp[:] = x
+    for xb, yb in ((xp, yp), (x.copy(), np.zeros(A.M))):
+        for hd, kernels in ((h, (4, 2, 1)), (hh, (2, 3))):
+            for kernel in kernels:
+                yb[:] = np.nan
+                ms = hd.spmv_host(xb, yb, kernel=kernel)
+                assert ms > 0
+                ok, worst = O.check_tolerance(yb, y_ref, bound, TOL)
+                assert ok, (type(hd).__name__, kernel, worst)
+    sp.pinned_free(xp)
+    sp.pinned_free(yp)
+    h.close()
+    hh.close()
+    sp.release_all()
+
+
+# --------------------------------------- full-size parity: BASELINE configs[2], [3] ------
+def _full_size(sp, O, torch, A, kernels_csr, hll, label):
+    x = np.random.default_rng(2).uniform(0, 1, A.N)
+    IRP, JA, AS = A.IRP, A.JA, A.AS
+    if O.ref_available():          # the reference's own serial CSR (oracle/_ref)
+        _, y_ref = O.ref_csr_serial(O.RefCsr(A.M, A.N, IRP, JA, AS), x)
+    else:
+        y_ref = O.csr_spmv(A.M, IRP, JA, AS, x)
+    bound = O.csr_abs_bound(A.M, IRP, JA, AS, x)
+    h = sp.CsrDevice.from_host(A)
+    xd = dev(torch, x)
+    y = torch.zeros(A.M, dtype=torch.float64, device="cuda")
+    for kernel in kernels_csr:
+        y.fill_(float("nan"))
+        h.spmv(xd, y, kernel=kernel, warps_per_block=8)
+        ok, worst = O.check_tolerance(y.cpu().numpy(), y_ref, bound, TOL)
+        assert ok, (label, "csr", kernel, worst)
+    # size-independent property: row sums (x = 1) equal the sums of the stored values
+    ones = torch.ones(A.N, dtype=torch.float64, device="cuda")
+    h.spmv(ones, y, kernel=2)
+    cs = np.concatenate([[0.0], np.cumsum(AS)])
+    rowsum = cs[IRP[1:]] - cs[IRP[:-1]]
+    absum = O.csr_abs_bound(A.M, IRP, JA, AS, np.ones(A.N))
+    assert (np.abs(y.cpu().numpy() - rowsum) <= 1e-9 * np.maximum(absum, 1.0)).all()
+    if hll:
+        hh = h.to_hll()
+        y.fill_(float("nan"))
+        hh.spmv(xd, y, kernel=2, warps_per_block=8)
+        ok, worst = O.check_tolerance(y.cpu().numpy(), y_ref, bound, TOL)
+        assert ok, (label, "hll", worst)
+        hh.close()
+    info = h.sell_info()
+    h.close()
+    return info
+
+
+def test_c3_full_size_parity(sp, O, torch):
+    """BASELINE configs[2]: uniform random n = 16 M, 32 per row (512 M entries), CSR ids 2 / 4 and
+    HLL id 2 against the reference's serial CSR.  x (128 MB) does not fit the L2: the library must
+    have chosen column panels on its own."""
+    A = sp.gen_uniform_random(16000000, 32, 42)
+    assert (A.M, A.NZ) == (16000000, 512000000)
+    info = _full_size(sp, O, torch, A, (2, 4), True, "c3")
+    assert info["state"] == 1 and info["panels"] > 1
+
+
+def test_c4_full_size_parity(sp, O, torch):
+    """BASELINE configs[3]: R-MAT scale 24, 16 edges per vertex (268 M entries, duplicates kept),
+    CSR ids 2 / 4 against the reference's serial CSR."""
+    A = sp.gen_rmat(24, 16)
+    assert (A.M, A.NZ) == (1 << 24, 1 << 28)
+    info = _full_size(sp, O, torch, A, (2, 4), False, "c4")
+    assert info["state"] == 1

@@ -133,16 +133,66 @@ def test_random_ragged_matrices(sp, O):
 
 
 def test_y_is_fully_overwritten_and_cache_sees_new_values(sp, O):
-    """The entry points must not depend on y being pre-zeroed, and a matrix whose values
-    change in place (same pointers) must not be served from the device cache."""
-    A = sp.gen_poisson2d(40, 40)
+    """The entry points must not depend on y being pre-zeroed, and a matrix that is edited in
+    place (same pointers, same shape) must never be served stale from the device cache: with the
+    default policy ("hash": the caller's arrays are re-hashed in full on every call) a change of
+    ONE value or ONE column index anywhere in the arrays is seen."""
+    A = sp.gen_stencil27(40, 40, 40)          # 1.7 M entries: far more than any sampled probe
     x = np.linspace(-1, 1, A.N)
-    _, _, y0 = sp.bench_csr_cuda_halfwarp_row(A, x, 4)
-    A.AS[:] *= 3.0
-    _, _, y1 = sp.bench_csr_cuda_halfwarp_row(A, x, 4)
-    assert_parity(O, y1, A.M, A.N, A.IRP.copy(), A.JA.copy(), A.AS.copy(), x, "cache-refresh")
-    assert not np.allclose(y0, y1)
+    args = lambda: (A.M, A.N, A.IRP.copy(), A.JA.copy(), A.AS.copy(), x)
+    H = sp.csr_to_hll(A, True)
+    for fname, mat in (("bench_csr_cuda_halfwarp_row", A), ("bench_csr_cuda_halfwarp_row_text", A)):
+        _, _, y0 = getattr(sp, fname)(mat, x, 4)
+        assert_parity(O, y0, *args(), "fresh")
+        k = 1234567
+        row = int(np.searchsorted(A.IRP, k, side="right") - 1)
+        old = A.AS[k]
+        A.AS[k] = 123.456                     # ONE value
+        _, _, y1 = getattr(sp, fname)(mat, x, 4)
+        assert_parity(O, y1, *args(), "one value edited in place")
+        assert y1[row] != y0[row] and np.array_equal(np.delete(y1, row), np.delete(y0, row))
+        oldc = A.JA[k]
+        A.JA[k] = (oldc + 777) % A.N          # ONE column index
+        _, _, y2 = getattr(sp, fname)(mat, x, 4)
+        assert_parity(O, y2, *args(), "one column index edited in place")
+        A.AS[k], A.JA[k] = old, oldc
+    # HLL: one value inside one hack
+    _, _, z0 = sp.bench_hll_cuda_warp_block(H, x, 4)
+    blk = H.block(777)
+    blk[5][3] = 9.75
+    _, _, z1 = sp.bench_hll_cuda_warp_block(H, x, 4)
+    assert not np.array_equal(z0, z1)
+    Hr, Hw, Hn, Ho, Hj, Ha = H.flat()
+    y_h = O.hll_spmv(A.M, Hr, Hw, Ho, True, O.hll_patch_pads(Hr, Hw, Ho, True, Hj), Ha, x)
+    bound = O.csr_abs_bound(*args()[:1], *args()[2:5], x) + 10 * np.abs(x).max()
+    ok, worst = O.check_tolerance(z1, y_h, bound, TOL)
+    assert ok, worst
     sp.release_all()
+
+
+def test_cache_policies(sp, O):
+    """"trust": pointers + shape are the key, spmv_b200_invalidate() after an in-place edit;
+    "off": a fresh upload per call (the reference's behaviour)."""
+    A = sp.gen_poisson2d(60, 60)
+    x = np.linspace(-1, 1, A.N)
+    try:
+        sp.set_cache_policy("trust")
+        _, _, y0 = sp.bench_csr_cuda_halfwarp_row(A, x, 4)
+        A.AS[:] *= 3.0
+        _, _, y_stale = sp.bench_csr_cuda_halfwarp_row(A, x, 4)
+        assert np.array_equal(y_stale, y0)            # by contract: the caller did not invalidate
+        sp.invalidate(A)
+        _, _, y1 = sp.bench_csr_cuda_halfwarp_row(A, x, 4)
+        assert_parity(O, y1, A.M, A.N, A.IRP.copy(), A.JA.copy(), A.AS.copy(), x, "after invalidate")
+        sp.set_cache_policy("off")
+        A.AS[:] *= 0.5
+        c0 = sp.counters()["h2d_bytes"]
+        _, _, y2 = sp.bench_csr_cuda_halfwarp_row(A, x, 4)
+        assert_parity(O, y2, A.M, A.N, A.IRP.copy(), A.JA.copy(), A.AS.copy(), x, "policy off")
+        assert sp.counters()["h2d_bytes"] - c0 >= 12 * A.NZ   # the matrix went up again
+    finally:
+        sp.set_cache_policy("hash")
+        sp.release_all()
 
 
 def test_timer_c_api(sp):
@@ -160,43 +210,50 @@ def test_timer_c_api(sp):
     L.spmv_b200_dfree(buf)
 
 
-def test_pipelined_entry_with_pinned_buffers(sp, O):
-    """Banded matrix + page-locked x / y: the CSR entry points upload x in column order, run row
-    chunks as their columns arrive and send y chunks back meanwhile.  Same results as the plain
-    path, for both chunkable kernels, with and without separately timed repetitions; a
-    non-banded matrix with pinned buffers must quietly take the plain path."""
+def test_host_buffer_pipeline(sp, O):
+    """Host x in / host y out.  Banded matrix: x goes up in column order, row chunks run as their
+    columns arrive, y chunks travel back meanwhile; page-locked caller buffers are used in place,
+    pageable ones (what the reference's compute_benchmark_csr hands over: posix_memalign vectors,
+    src/vector.c:11-20) go through the library's bounce buffers.  Same results as the plain path,
+    CSR and HLL entry points, with and without separately timed repetitions; a non-banded matrix
+    takes the unchunked pass."""
     import ctypes as C
     L = sp._lib.b200
-
-    def pinned(n):
-        p = L.spmv_b200_host_alloc(max(n, 1) * 8)
-        assert p
-        return p, np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(n,))
+    dp = C.POINTER(C.c_double)
 
     for make, banded in ((lambda: sp.gen_stencil27(64, 64, 64), True),
                          (lambda: sp.gen_uniform_random(300000, 16, 5), False)):
         A = make()
-        px, xh = pinned(A.N)
-        py, yh = pinned(A.M)
-        xh[:] = np.random.default_rng(8).uniform(-1, 1, A.N)
+        Hc, Hr = sp.csr_to_hll(A, True), sp.csr_to_hll(A, False)
+        x_src = np.random.default_rng(8).uniform(-1, 1, A.N)
         IRP, JA, AS = A.IRP.copy(), A.JA.copy(), A.AS.copy()
-        y_ref = oracle_y(O, A.M, A.N, IRP, JA, AS, xh.copy())
-        bound = O.csr_abs_bound(A.M, IRP, JA, AS, xh.copy())
-        dp = C.POINTER(C.c_double)
-        for fn in (L.csr_spmv_cuda_halfwarp_row, L.csr_spmv_cuda_halfwarp_row_text, L.csr_spmv_cuda_warp_row):
-            for reps in (0, 2):
-                sp.set_timing(1, reps)
-                L.set_csr_warps_per_block(4)
-                yh[:] = np.nan
-                c0 = sp.counters()
-                ms = fn(A.ptr, C.cast(px, dp), C.cast(py, dp), None)
-                c1 = sp.counters()
-                assert ms > 0, sp._lib.last_error()
-                ok, worst = O.check_tolerance(yh, y_ref, bound, TOL)
-                assert ok, (banded, fn.__name__, reps, worst)
-                assert c1["h2d_bytes"] - c0["h2d_bytes"] >= 8 * A.N     # x went up (plus plans on first use)
-                assert c1["d2h_bytes"] - c0["d2h_bytes"] == 8 * A.M
+        y_ref = oracle_y(O, A.M, A.N, IRP, JA, AS, x_src)
+        bound = O.csr_abs_bound(A.M, IRP, JA, AS, x_src)
+        for pinned in (True, False):
+            if pinned:
+                xh, yh = sp.pinned_empty(A.N), sp.pinned_empty(A.M)
+            else:
+                xh, yh = sp.aligned_array(A.N), sp.aligned_array(A.M)
+            xh[:] = x_src
+            calls = [(L.csr_spmv_cuda_halfwarp_row, A), (L.csr_spmv_cuda_halfwarp_row_text, A),
+                     (L.csr_spmv_cuda_warp_row, A), (L.hll_spmv_cuda_warp_block, Hc),
+                     (L.hll_spmv_cuda_threads_col_major, Hc), (L.hll_spmv_cuda_halfwarp_row, Hr)]
+            for fn, mat in calls:
+                for reps in (0, 2):
+                    sp.set_timing(1, reps)
+                    L.set_csr_warps_per_block(4)
+                    L.set_hll_warps_per_block(4)
+                    yh[:] = np.nan
+                    c0 = sp.counters()
+                    ms = fn(mat.ptr, xh.ctypes.data_as(dp), yh.ctypes.data_as(dp), None)
+                    c1 = sp.counters()
+                    assert ms > 0, sp._lib.last_error()
+                    ok, worst = O.check_tolerance(yh, y_ref, bound, TOL)
+                    assert ok, (banded, pinned, fn.__name__, reps, worst)
+                    assert c1["h2d_bytes"] - c0["h2d_bytes"] >= 8 * A.N     # x went up (plus plans on first use)
+                    assert c1["d2h_bytes"] - c0["d2h_bytes"] >= 8 * A.M
+            if pinned:
+                sp.pinned_free(xh)
+                sp.pinned_free(yh)
         sp.set_timing(1, 3)
         sp.release_all()
-        L.spmv_b200_host_free(px)
-        L.spmv_b200_host_free(py)

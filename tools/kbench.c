@@ -24,6 +24,7 @@
 #include "spmv_gen.h"
 
 static int g_reps = 20, g_warmup = 3, g_flush = 0, g_quick = 0, g_profile = 0, g_cfg_from = -1;
+static int g_sell = 0;
 static double g_peak = 6559.7; /* MEASURED_PEAKS.json hbm_gbs of this pool */
 static const char *g_only = "";
 
@@ -151,6 +152,8 @@ int main(int argc, char **argv) {
                         spmv_b200_set_knob(key, val);
             } else if (!strcmp(argv[i], "--profile"))
                   g_profile = 1; /* only the headline kernels: for ncu captures */
+            else if (!strcmp(argv[i], "--sell"))
+                  g_sell = 1; /* SELL-P sweep: panels x sigma x warps/block, CSR and HLL source */
       }
       spmv_b200_devinfo info;
       if (spmv_b200_device_info(&info)) {
@@ -198,6 +201,80 @@ int main(int argc, char **argv) {
 
       static const int wpbs[] = {2, 4, 8, 16};
       char knob[64];
+
+      if (g_sell) {
+            static const int panels[] = {1, 2, 3, 4, 6, 8, 16};
+            static const int sigmas[] = {1024, 16384, 262144};
+            int64_t info[8];
+            /* what the library picks on its own, then the old paths, then the sweep */
+            spmv_b200_csr *h = spmv_b200_csr_create(A);
+            if (!h) {
+                  fprintf(stderr, "kbench: %s\n", spmv_b200_last_error());
+                  return 1;
+            }
+            for (int w = 1; w < 4; ++w)
+                  run_csr(&c, h, 2, wpbs[w], "auto");
+            spmv_b200_csr_sell_info(h, 0, info, 8);
+            printf("# auto: sell state=%lld panels=%lld sigma=%lld slots=%lld (padding %.2f%%) long_rows=%lld "
+                   "gather_span=%.3f\n", (long long)info[0], (long long)info[1], (long long)info[2],
+                   (long long)info[4], info[5] ? 100.0 * (info[4] - (double)info[5]) / info[5] : 0.0,
+                   (long long)info[6], info[7] * 1e-6);
+            run_csr(&c, h, 4, 4, "auto");
+            spmv_b200_set_knob("sell", 0);
+            run_csr(&c, h, 2, 8, "sell=0");
+            run_csr(&c, h, 4, 4, "sell=0");
+            spmv_b200_csr_destroy(h);
+            spmv_b200_set_knob("sell", 1);
+            for (int ip = 0; ip < 7; ++ip) {
+                  for (int is = 0; is < 3; ++is) {
+                        if (is != 1 && !(panels[ip] == 1 || panels[ip] == 4))
+                              continue; /* sigma only matters for padding: sweep it at two panel counts */
+                        spmv_b200_set_knob("sell_panels", panels[ip]);
+                        spmv_b200_set_knob("sell_sigma", sigmas[is]);
+                        h = spmv_b200_csr_create(A);
+                        if (!h || spmv_b200_csr_sell_info(h, 1, info, 8) || info[0] != 1) {
+                              printf("CSR  sell panels=%d sigma=%d BUILD FAILED: %s\n", panels[ip],
+                                     sigmas[is], spmv_b200_last_error());
+                              spmv_b200_csr_destroy(h);
+                              continue;
+                        }
+                        snprintf(knob, sizeof knob, "K=%d s=%d pad=%.1f%%", panels[ip], sigmas[is],
+                                 info[5] ? 100.0 * (info[4] - (double)info[5]) / info[5] : 0.0);
+                        for (int w = 1; w < 4; ++w)
+                              if (is == 1 || w == 2)
+                                    run_csr(&c, h, 2, wpbs[w], knob);
+                        spmv_b200_csr_destroy(h);
+                  }
+            }
+            if (strcmp(g_only, "csr")) {
+                  spmv_b200_set_knob("sell_sigma", 16384);
+                  spmv_b200_csr *hc = spmv_b200_csr_create(A);
+                  for (int ip = -1; ip < 7; ++ip) {
+                        spmv_b200_set_knob("sell", ip < 0 ? 0 : 1);
+                        spmv_b200_set_knob("sell_panels", ip < 0 ? 0 : panels[ip]);
+                        spmv_b200_hll *hh = hc ? spmv_b200_hll_from_csr(hc) : NULL;
+                        if (!hh) {
+                              printf("HLL  build failed: %s\n", spmv_b200_last_error());
+                              break;
+                        }
+                        if (ip < 0)
+                              snprintf(knob, sizeof knob, "sell=0");
+                        else
+                              snprintf(knob, sizeof knob, "K=%d", panels[ip]);
+                        run_hll(&c, hh, 2, 8, knob);
+                        if (ip < 0) {
+                              spmv_b200_set_knob("hll_vec", 4);
+                              run_hll(&c, hh, 2, 16, "sell=0 vec=4");
+                              spmv_b200_set_knob("hll_vec", -1);
+                        }
+                        spmv_b200_hll_destroy(hh);
+                  }
+                  spmv_b200_csr_destroy(hc);
+            }
+            spmv_b200_set_knob("sell", -1);
+            spmv_b200_set_knob("sell_panels", 0);
+            return 0;
+      }
 
       if (g_profile) {
             spmv_b200_csr *h = spmv_b200_csr_create(A);
@@ -252,17 +329,19 @@ int main(int argc, char **argv) {
             spmv_b200_set_knob("adaptive_direct", 1);
             for (int w = 0; w < 3; ++w)
                   run_csr(&c, h, 2, wpbs[w], "direct-binned");
-            spmv_b200_set_knob("stream_hints", 0);
-            run_csr(&c, h, 2, 8, "direct,nohints");
-            spmv_b200_set_knob("stream_hints", 1);
             spmv_b200_set_knob("adaptive_direct", 0);
             for (int w = 0; w < 3; ++w)
                   run_csr(&c, h, 4, wpbs[w], "auto");
-            for (int cfg = g_cfg_from >= 0 ? g_cfg_from : (g_quick ? 10 : 0); cfg < 35; ++cfg) {
-                  spmv_b200_set_knob("csr_stream_cfg", cfg);
-                  snprintf(knob, sizeof knob, "cfg=%d", cfg);
+            static const int cfgs[] = {10, 12, 13, 24, 25, 26, 33};
+            spmv_b200_set_knob("sell", 0); /* the staged kernel itself, whatever the matrix */
+            for (int i = 0; i < 7; ++i) {
+                  if (cfgs[i] < g_cfg_from)
+                        continue;
+                  spmv_b200_set_knob("csr_stream_cfg", cfgs[i]);
+                  snprintf(knob, sizeof knob, "cfg=%d", cfgs[i]);
                   run_csr(&c, h, 4, 4, knob);
             }
+            spmv_b200_set_knob("sell", -1);
             spmv_b200_set_knob("csr_stream_cfg", -1);
             spmv_b200_csr_destroy(h);
             if (!g_quick) {
@@ -302,7 +381,7 @@ int main(int argc, char **argv) {
                         run_hll(&c, hh, 2, wpbs[w], knob);
             }
             spmv_b200_set_knob("hll_vec", -1);
-            for (int cfg = 0; cfg < 6; ++cfg) {
+            for (int cfg = 0; cfg < 3; ++cfg) {
                   spmv_b200_set_knob("hll_stream_cfg", cfg);
                   snprintf(knob, sizeof knob, "cfg=%d", cfg);
                   run_hll(&c, hh, 3, 4, knob);
