@@ -354,3 +354,155 @@ int orc_max_threads(void) {
       return 1;
 #endif
 }
+
+/* ------------------------------------------------ synthetic inputs (oracle side) */
+/* bench.py --impl reference must not map any product library, so the BASELINE.json
+ * inputs are restated here: same definitions as include/spmv_gen.h (the reference
+ * itself has no generators -- it downloads SuiteSparse files,
+ * scripts/download-matrices.py).  tests/test_generators.py checks that both sides
+ * produce identical arrays.  Callers size the arrays with the *_nnz helpers. */
+
+static uint64_t orc_mix64(uint64_t z) { /* splitmix64 finaliser */
+      z += 0x9E3779B97F4A7C15ull;
+      z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+      z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+      return z ^ (z >> 31);
+}
+static uint64_t orc_draw(uint64_t seed, uint64_t a, uint64_t b) {
+      return orc_mix64(orc_mix64(seed ^ (a * 0xD1342543DE82EF95ull)) + b);
+}
+static double orc_pm1(uint64_t bits) {
+      return ((double)(bits >> 11) + 0.5) * (2.0 / 9007199254740992.0) - 1.0;
+}
+static int orc_span(int c, int n) { return 1 + (c > 0) + (c < n - 1); }
+
+/* 27-point stencil, rows [row0,row1): entries of those rows (global columns). */
+int64_t orc_stencil27_nnz(int nx, int ny, int nz, int64_t row0, int64_t row1) {
+      const int64_t plane = (int64_t)nx * ny;
+      int64_t nnz = 0;
+#pragma omp parallel for reduction(+ : nnz) schedule(static)
+      for (int64_t g = row0; g < row1; ++g)
+            nnz += (int64_t)orc_span((int)(g % nx), nx) * orc_span((int)(g / nx % ny), ny) *
+                   orc_span((int)(g / plane), nz);
+      return nnz;
+}
+
+void orc_gen_stencil27_rows(int nx, int ny, int nz, int64_t row0, int64_t row1, int *irp, int *ja,
+                            double *as) {
+      const int64_t plane = (int64_t)nx * ny, rows = row1 - row0;
+      irp[0] = 0;
+      for (int64_t r = 0; r < rows; ++r) {
+            const int64_t g = row0 + r;
+            irp[r + 1] = irp[r] + orc_span((int)(g % nx), nx) * orc_span((int)(g / nx % ny), ny) *
+                                      orc_span((int)(g / plane), nz);
+      }
+#pragma omp parallel for schedule(static)
+      for (int64_t r = 0; r < rows; ++r) {
+            const int64_t g = row0 + r;
+            const int ix = (int)(g % nx), iy = (int)(g / nx % ny), iz = (int)(g / plane);
+            int k = irp[r];
+            for (int dz = -1; dz <= 1; ++dz)
+                  for (int dy = -1; dy <= 1; ++dy)
+                        for (int dx = -1; dx <= 1; ++dx) {
+                              if (iz + dz < 0 || iz + dz >= nz || iy + dy < 0 || iy + dy >= ny ||
+                                  ix + dx < 0 || ix + dx >= nx)
+                                    continue;
+                              ja[k] = (int)(g + dz * plane + dy * nx + dx);
+                              as[k] = (dz | dy | dx) ? -1.0 : 26.0;
+                              ++k;
+                        }
+      }
+}
+
+/* 2D 5-point Laplacian (diag 4, neighbours -1), nnz = 5n - 2nx - 2ny. */
+void orc_gen_poisson2d(int nx, int ny, int *irp, int *ja, double *as) {
+      int k = 0;
+      for (int iy = 0; iy < ny; ++iy)
+            for (int ix = 0; ix < nx; ++ix) {
+                  const int r = iy * nx + ix;
+                  irp[r] = k;
+                  if (iy > 0)
+                        ja[k] = r - nx, as[k++] = -1.0;
+                  if (ix > 0)
+                        ja[k] = r - 1, as[k++] = -1.0;
+                  ja[k] = r, as[k++] = 4.0;
+                  if (ix < nx - 1)
+                        ja[k] = r + 1, as[k++] = -1.0;
+                  if (iy < ny - 1)
+                        ja[k] = r + nx, as[k++] = -1.0;
+            }
+      irp[nx * ny] = k;
+}
+
+static int orc_cmp_int(const void *a, const void *b) {
+      const int x = *(const int *)a, y = *(const int *)b;
+      return (x > y) - (x < y);
+}
+
+/* Rows [row0,row1) of the n x n uniform-random matrix with k distinct sorted columns per row. */
+void orc_gen_uniform_rows(int n, int k, uint64_t seed, int row0, int row1, int *irp, int *ja,
+                          double *as) {
+      for (int r = row0; r <= row1; ++r)
+            irp[r - row0] = (int)((int64_t)(r - row0) * k);
+#pragma omp parallel for schedule(static, 4096)
+      for (int r = row0; r < row1; ++r) {
+            int *cols = ja + (size_t)(r - row0) * k;
+            double *vals = as + (size_t)(r - row0) * k;
+            int have = 0;
+            for (uint64_t t = 0; have < k; ++t) {
+                  const int c = (int)(orc_draw(seed, (uint64_t)r, t) % (uint64_t)n);
+                  int dup = 0;
+                  for (int q = 0; q < have; ++q)
+                        dup |= cols[q] == c;
+                  if (!dup)
+                        cols[have++] = c;
+            }
+            qsort(cols, (size_t)k, sizeof *cols, orc_cmp_int);
+            for (int j = 0; j < k; ++j)
+                  vals[j] = orc_pm1(orc_draw(seed ^ 0xA5A5A5A5A5A5A5A5ull, (uint64_t)r, (uint64_t)j));
+      }
+}
+
+/* R-MAT, 2^scale vertices, edge_factor * 2^scale edges, duplicates kept, rows in edge order.
+ * 0 or -ENOMEM. */
+int orc_gen_rmat(int scale, int edge_factor, double a, double b, double c, uint64_t seed, int *irp,
+                 int *ja, double *as) {
+      const int64_t n = (int64_t)1 << scale, m = n * edge_factor;
+      int *src = malloc((size_t)m * sizeof *src), *dst = malloc((size_t)m * sizeof *dst);
+      int *cursor = calloc((size_t)n + 1, sizeof *cursor);
+      if (!src || !dst || !cursor) {
+            free(src), free(dst), free(cursor);
+            return -ENOMEM;
+      }
+      const uint64_t ta = (uint64_t)(a * 4294967296.0), tab = (uint64_t)((a + b) * 4294967296.0),
+                     tabc = (uint64_t)((a + b + c) * 4294967296.0);
+#pragma omp parallel for schedule(static, 65536)
+      for (int64_t e = 0; e < m; ++e) {
+            int i = 0, j = 0;
+            uint64_t bits = 0;
+            for (int lvl = 0; lvl < scale; ++lvl) {
+                  if ((lvl & 1) == 0)
+                        bits = orc_draw(seed, (uint64_t)e, (uint64_t)(lvl >> 1));
+                  const uint64_t u = bits & 0xFFFFFFFFull;
+                  bits >>= 32;
+                  const int q = (u >= ta) + (u >= tab) + (u >= tabc);
+                  i = (i << 1) | (q >> 1);
+                  j = (j << 1) | (q & 1);
+            }
+            src[e] = i, dst[e] = j;
+      }
+      for (int64_t e = 0; e < m; ++e)
+            ++cursor[src[e] + 1];
+      irp[0] = 0;
+      for (int64_t r = 0; r < n; ++r) {
+            irp[r + 1] = irp[r] + cursor[r + 1];
+            cursor[r] = irp[r];
+      }
+      for (int64_t e = 0; e < m; ++e) {
+            const int k = cursor[src[e]]++;
+            ja[k] = dst[e];
+            as[k] = orc_pm1(orc_draw(seed ^ 0x5A5A5A5A5A5A5A5Aull, (uint64_t)e, 0xC0FFEEull));
+      }
+      free(src), free(dst), free(cursor);
+      return 0;
+}

@@ -85,6 +85,14 @@ def port():
         lib.orc_csr_spmv_timed.restype = C.c_double
         lib.orc_csr_spmv_timed.argtypes = [C.c_int, _ip, _ip, _dp, _dp, _dp, C.c_int]
         lib.orc_max_threads.restype = C.c_int
+        lib.orc_stencil27_nnz.restype = C.c_int64
+        lib.orc_stencil27_nnz.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64]
+        lib.orc_gen_stencil27_rows.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, _ip, _ip, _dp]
+        lib.orc_gen_poisson2d.argtypes = [C.c_int, C.c_int, _ip, _ip, _dp]
+        lib.orc_gen_uniform_rows.argtypes = [C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int, _ip, _ip, _dp]
+        lib.orc_gen_rmat.restype = C.c_int
+        lib.orc_gen_rmat.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_uint64,
+                                     _ip, _ip, _dp]
         _port = lib
     return _port
 
@@ -255,6 +263,46 @@ def hll_spmv(M, rows, width, off, col_major, ja, as_, x):
                         _ci(np.ascontiguousarray(ja, np.int32)),
                         _cd(np.ascontiguousarray(as_, np.float64)), _cd(x), _cd(y))
     return y[:M]
+
+
+# ---- synthetic inputs, oracle side (same definitions as include/spmv_gen.h) ----
+def gen_stencil27_rows(nx, ny, nz, row0, row1):
+    """(M, N, IRP, JA, AS) of rows [row0,row1) of the 27-point stencil, global columns."""
+    nnz = port().orc_stencil27_nnz(nx, ny, nz, row0, row1)
+    assert nnz < 2**31
+    M = row1 - row0
+    IRP, JA, AS = aligned(M + 1, np.int32), aligned(nnz, np.int32), aligned(nnz, np.float64)
+    port().orc_gen_stencil27_rows(nx, ny, nz, row0, row1, _ci(IRP), _ci(JA), _cd(AS))
+    return M, nx * ny * nz, IRP, JA, AS
+
+
+def gen_stencil27(nx, ny, nz):
+    return gen_stencil27_rows(nx, ny, nz, 0, nx * ny * nz)
+
+
+def gen_poisson2d(nx, ny):
+    n = nx * ny
+    nnz = 5 * n - 2 * nx - 2 * ny
+    IRP, JA, AS = aligned(n + 1, np.int32), aligned(nnz, np.int32), aligned(nnz, np.float64)
+    port().orc_gen_poisson2d(nx, ny, _ci(IRP), _ci(JA), _cd(AS))
+    return n, n, IRP, JA, AS
+
+
+def gen_uniform_rows(n, k, seed, row0, row1):
+    M = row1 - row0
+    IRP, JA, AS = aligned(M + 1, np.int32), aligned(M * k, np.int32), aligned(M * k, np.float64)
+    port().orc_gen_uniform_rows(n, k, seed, row0, row1, _ci(IRP), _ci(JA), _cd(AS))
+    return M, n, IRP, JA, AS
+
+
+def gen_rmat(scale, edge_factor=16, a=0.57, b=0.19, c=0.19, seed=42):
+    n = 1 << scale
+    m = n * edge_factor
+    IRP, JA, AS = aligned(n + 1, np.int32), aligned(m, np.int32), aligned(m, np.float64)
+    rc = port().orc_gen_rmat(scale, edge_factor, a, b, c, seed, _ci(IRP), _ci(JA), _cd(AS))
+    if rc:
+        raise MemoryError("orc_gen_rmat")
+    return n, n, IRP, JA, AS
 
 
 def partition_rows(M, IRP, parts):
@@ -502,3 +550,81 @@ def ref_rand_x(n):
     out = np.ctypeslib.as_array(v.data, shape=(max(n, 1),))[:n].copy()
     ref().vec_put(C.byref(v))
     return out
+
+
+# ------------------------------------ the reference's own CUDA kernels on this GPU --
+class _bench_cuda(C.Structure):
+    _fields_ = [("bench", _bench), ("warps_per_block", C.c_int)]
+
+
+def ref_cuda_available():
+    return os.path.exists(os.path.join(HERE, "_ref", "libspmv_ref_cuda.so"))
+
+
+def ref_cuda_bench(M, N, IRP, JA, AS, x, reps=5, wpbs=(4, 8)):
+    """Times the reference's UNMODIFIED kernels (src/cuda_csr.cu, src/cuda_hll.cu rebuilt for
+    sm_100a by oracle/Makefile) through the reference's own bench_*_cuda_* trampolines
+    (src/csr.c:382-415, src/hll.c:226-256): every call uploads, runs ONE launch between CUDA events,
+    downloads (src/cuda_csr.cu:210-233).  Must run in a process that has NOT loaded libspmv_b200
+    (both export csr_spmv_cuda_*): bench.py calls `python -m oracle.oracle refcuda ...`.
+    Returns {name: {"ms_min", "ms_median", "gflops_best", "ok"}}."""
+    lib = C.CDLL(os.path.join(HERE, "_ref", "libspmv_ref_cuda.so"))
+    lib.csr_to_hll.restype = C.c_void_p
+    lib.csr_to_hll.argtypes = [C.POINTER(_csr), C.c_bool]
+    lib.hll_free.argtypes = [C.c_void_p]
+    lib.vec_put.argtypes = [C.POINTER(_vec)]
+    A = RefCsr(M, N, IRP, JA, AS)
+    xa = aligned_copy(x, np.float64)
+    y_ref = csr_spmv(M, IRP, JA, AS, x)
+    bound = csr_abs_bound(M, IRP, JA, AS, x)
+    out = {}
+    nnz = len(JA)
+
+    def run(fname, mat_ptr, label):
+        fn = getattr(lib, fname)
+        fn.argtypes = [C.c_void_p, _dp, C.POINTER(_bench_cuda)]
+        for wpb in wpbs:
+            ms, ok = [], True
+            for _ in range(reps):
+                b = _bench_cuda()
+                b.warps_per_block = wpb
+                rc = fn(mat_ptr, _cd(xa), C.byref(b))
+                if rc:
+                    ok = False
+                    break
+                n = b.bench.data.len
+                y = np.ctypeslib.as_array(b.bench.data.data, shape=(max(n, 1),))[:n].copy()
+                lib.vec_put(C.byref(b.bench.data))
+                ms.append(b.bench.duration_ms)
+                ok = ok and check_tolerance(y, y_ref, bound, 1e-12)[0]
+            if ms and min(ms) > 0:
+                out[f"{label}_wpb{wpb}"] = {"ms_min": min(ms), "ms_median": sorted(ms)[len(ms) // 2],
+                                            "gflops_best": 2.0 * nnz / (min(ms) * 1e6), "ok": bool(ok)}
+
+    import ctypes
+    a_ptr = ctypes.cast(A.ptr, C.c_void_p)
+    run("bench_csr_cuda_halfwarp_row", a_ptr, "csr_k2_halfwarp_row")
+    run("bench_csr_cuda_warp_row", a_ptr, "csr_k1_warp_row")
+    if nnz <= 100_000_000:     # the reference's HLL upload does 2 cudaMalloc + 3 cudaMemcpy per hack and call
+        Hc = lib.csr_to_hll(A.ptr, True)
+        if not _is_err(Hc):
+            run("bench_hll_cuda_threads_col_major", C.c_void_p(Hc), "hll_k1_threads_col_major")
+            run("bench_hll_cuda_warp_block", C.c_void_p(Hc), "hll_k2_warp_block")
+            lib.hll_free(Hc)
+    return out
+
+
+if __name__ == "__main__":
+    import json
+    if len(sys.argv) >= 3 and sys.argv[1] == "refcuda":
+        spec = sys.argv[2]
+        if spec == "c2":
+            M, N, IRP, JA, AS = gen_stencil27(128, 128, 128)
+        elif spec == "c1":
+            M, N, IRP, JA, AS = gen_poisson2d(1000, 1000)
+        elif spec == "tiny":
+            M, N, IRP, JA, AS = gen_stencil27(24, 24, 24)
+        else:
+            raise SystemExit("refcuda: c1 | c2 | tiny")
+        x = np.random.default_rng(0).uniform(0, 1, N)
+        print(json.dumps(ref_cuda_bench(M, N, IRP, JA, AS, x)))

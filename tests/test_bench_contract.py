@@ -43,17 +43,36 @@ def test_b200_arm_line():
     assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and rf["peak"] > 1000
     assert abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
     assert d["gpu_launches"] >= d["steps"]
-    e = d["e2e"]
+    e = d["e2e"]                            # headline: pageable caller buffers; pinned as a sub-key
     assert e["value"] > 0 and e["h2d_bytes_per_step"] == 8 * d["config"]["cols"] and e["d2h_bytes_per_step"] == 8 * d["config"]["rows"]
     assert e["value"] < d["value"]            # the host round trip cannot be free
+    assert e["pinned"]["value"] > 0 and e["pinned"]["h2d_bytes_per_step"] == 8 * d["config"]["cols"]
     assert d["cpu_baseline"]["value"] > 0
     assert d["config"]["parity"]["csr"]["ok"] and d["config"]["parity"]["hll"]["ok"]
     assert "sm_mhz" in d["clocks"] and isinstance(d["clocks"]["reasons"], list)
 
 
+@pytest.mark.gpu
+def test_b200_default_path_line():
+    """The default path (bench_dist, one rank = one GPU) on the small slab workload: strong/weak
+    flag, repeated timed regions, stand-alone kernel before and after, both e2e variants."""
+    d = run_bench("--workload", "c2w", "--steps", "4", "--warmup", "3", "--regions", "3", "--configs", "none",
+                  "--no-cpu")
+    assert BASE_KEYS | {"roofline", "gpu_launches", "clocks", "regions_ms"} <= set(d)
+    assert d["n_gpus"] == 1 and d["scaling"] == "weak" and len(d["regions_ms"]) == 3
+    assert d["config"]["nnz"] == 55742968 and d["config"]["cuda_graph"] is True and d["config"]["finite"]
+    assert abs(d["ms_per_step"] * 4 - sorted(d["regions_ms"])[1]) < 1e-9
+    assert 0.3 < d["roofline"]["frac"] < 1.2
+    assert d["e2e"]["value"] > 0 and d["e2e"]["pinned"]["value"] >= 0.5 * d["e2e"]["value"]
+    assert d["parity"]["step1_vs_oracle"] is True
+    assert len(d["standalone_kernel_ms_by_rank"]["after_run_mean"]) == 1
+
+
 def test_reference_arm_under_torchrun_env():
-    """N>1: rank 0 alone prints the line, the other ranks exit 0 without work."""
-    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1", MASTER_ADDR="127.0.0.1", MASTER_PORT="29555")
+    """N>1: rank 0 alone prints the line, the other ranks exit 0 without work; torchrun's
+    OMP_NUM_THREADS=1 must not make the reference's OpenMP code run on one core."""
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1", MASTER_ADDR="127.0.0.1", MASTER_PORT="29555",
+               OMP_NUM_THREADS="1")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
                         "--workload", "tiny", "--steps", "2", "--warmup", "1"], capture_output=True, text=True,
                        timeout=300, cwd=ROOT, env=env)
@@ -66,3 +85,23 @@ def test_reference_arm_under_torchrun_env():
     assert r.returncode == 0
     d = json.loads(r.stdout.strip().splitlines()[-1])
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0
+    cores = len(os.sched_getaffinity(0))
+    assert d["cpu_baseline"]["host_cores"] == cores
+    if cores > 1:
+        assert d["cpu_baseline"]["variants"]["omp_guided"]["cores"] == cores
+        assert d["cpu_baseline"]["cores"] >= 1
+
+
+def test_reference_arm_maps_no_product_library():
+    """The CPU arm is the reference's code only: neither libspmv_b200 nor libspmv_host may be
+    mapped into its process (round-1 verdict: the arm generated its matrix with the product)."""
+    code = ("import sys, runpy\n"
+            "sys.argv = ['bench.py', '--impl', 'reference', '--workload', 'tiny', '--steps', '2', '--warmup', '1']\n"
+            "try:\n    runpy.run_path(%r, run_name='__main__')\nexcept SystemExit:\n    pass\n"
+            "print('MAPS', sorted({l.split()[-1] for l in open('/proc/self/maps') if '.so' in l and %r in l}))\n"
+            ) % (os.path.join(ROOT, "bench.py"), ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-1500:]
+    maps = [l for l in r.stdout.splitlines() if l.startswith("MAPS")][0]
+    assert "libspmv_b200" not in maps and "libspmv_host" not in maps, maps
+    assert "oracle" in maps
