@@ -94,11 +94,18 @@ def host_matrix(sp, workload):
             "tiny": lambda: sp.gen_stencil27(32, 32, 32)}[workload]()
 
 
-def host_cores():
+def _host_cores_now():
     try:
         return len(os.sched_getaffinity(0))
     except Exception:
         return os.cpu_count() or 1
+
+
+_HOST_CORES = _host_cores_now()   # taken at start-up: NCCL narrows the calling thread's mask during init
+
+
+def host_cores():
+    return _HOST_CORES
 
 
 # ------------------------------------------------------------------ clocks --
@@ -480,8 +487,14 @@ def run_single(args):
         "gpu_launches": head["launches_per_step"] * args.steps, "clocks": clocks,
         "formats": rec["formats"], "e2e_formats": rec["e2e"], "device": sp.device_info()["name"],
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
+
+
+def emit(line):
+    out = getattr(sys, "_bench_real_stdout", None) or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
@@ -505,6 +518,11 @@ def main():
 
     if args.impl == "reference":
         return run_reference_arm(args)
+    # ONE line on stdout: libraries that print there (NCCL's version banner ...) are sent to stderr
+    # while the run lasts; emit() writes the JSON line to the real stdout
+    sys.stdout.flush()
+    sys._bench_real_stdout = os.fdopen(os.dup(1), "w")   # on `sys`: bench_dist imports this file as a module
+    os.dup2(2, 1)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.workload in ("c5", "c2w") or args.gpus > 1 or world > 1:
         if args.workload not in ("c5", "c2w"):

@@ -51,7 +51,7 @@ def gather_lists(dist, torch, device, values):
 def run(args):
     import torch
     import torch.distributed as dist
-    from bench import (ClockSampler, DESCR, host_cores, measured_peak, ncu_traffic, roofline_bytes,
+    from bench import (ClockSampler, DESCR, emit, host_cores, measured_peak, ncu_traffic, roofline_bytes,
                        reference_gpu_rows, single_config, cpu_reference_run)
 
     rank = int(os.environ.get("RANK", "0"))
@@ -284,7 +284,7 @@ def run(args):
                             "on this GPU, C2 (128^3 stencil), one launch per call as the reference times it",
                     "rows": ref_gpu}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     dist.barrier()
     dist.destroy_process_group()
     return 0

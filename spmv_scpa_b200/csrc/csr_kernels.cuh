@@ -491,6 +491,8 @@ __global__ void __launch_bounds__(THREADS + (WS ? 32 : 0))
 
       const int gi = tid / LPR, sub = tid % LPR;
       int it = 0;
+      int n_split = 0; // entry-split tiles done so far: selects the long-row counter (tiles that
+                       // hold one oversized row are skipped and must not advance the alternation)
       for (int t = first; t < last; t += stride, ++it) {
             const int stage = it % STAGES;
             const uint32_t parity = (uint32_t)(it / STAGES) & 1u;
@@ -508,12 +510,14 @@ __global__ void __launch_bounds__(THREADS + (WS ? 32 : 0))
 
             if (SPLIT) {
                   const int cnt = (int)(((tile_k[t + 1] + 3) & ~3ll) - kbase);
-                  if (staged)
+                  if (staged) {
                         stream_tile_products<THREADS, PASSES, CAP, EPI, OffT>(
                             s_irp + (size_t)stage * Cfg::kIrpSlots, s_as + (size_t)stage * CAP,
                             s_ja + (size_t)stage * CAP, r0, r1, r0 & ~(IRP_ALIGN - 1), kbase, cnt,
-                            tid, x, y, pol_x, epi, dot_acc, s_queue, s_queue_n + (it & 1),
-                            s_queue_n + ((it + 1) & 1));
+                            tid, x, y, pol_x, epi, dot_acc, s_queue, s_queue_n + (n_split & 1),
+                            s_queue_n + ((n_split + 1) & 1));
+                        ++n_split;
+                  }
             } else if (staged) {
                   stream_tile_rows<LPR, RPP, PASSES, EPI, OffT>(
                       irp, s_as + (size_t)stage * CAP, s_ja + (size_t)stage * CAP, r0, r1, kbase,

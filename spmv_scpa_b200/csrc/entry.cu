@@ -13,6 +13,8 @@
 
 #include <omp.h>
 
+#include <functional>
+
 using namespace b200;
 
 namespace {
@@ -91,7 +93,7 @@ bool is_pinned(const void *p) {
 
 // memcpy spread over the OpenMP team (pageable <-> bounce buffer)
 void parallel_copy(void *dst, const void *src, size_t bytes) {
-      constexpr size_t kBlock = 1u << 20;
+      constexpr size_t kBlock = 256u << 10; // small enough that an 8 MiB piece feeds every core
       const long long blocks = (long long)((bytes + kBlock - 1) / kBlock);
       if (blocks <= 2) {
             memcpy(dst, src, bytes);
@@ -140,6 +142,7 @@ double host_pass(long long N, long long M, const double *x, double *y, int n,
       std::vector<Piece> downs;
       int rc = 0, n_out = 0;
       // 1. uploads of pinned x can be queued right away
+      std::function<void(bool)> drain; // set below, once the download list exists
       auto upload_range = [&](long long a, long long b) {
             for (long long p = a; p < b; p += kPiece) {
                   const long long q = std::min(b, p + kPiece);
@@ -150,6 +153,8 @@ double host_pass(long long N, long long M, const double *x, double *y, int n,
                   }
                   cudaMemcpyAsync(s->dx + p, src, (size_t)(q - p) * 8, cudaMemcpyHostToDevice,
                                   s->s_in);
+                  if (bounce_x && drain)
+                        drain(false);
             }
       };
       if (!bounce_x) {
@@ -160,9 +165,30 @@ double host_pass(long long N, long long M, const double *x, double *y, int n,
                   cudaEventRecord(s->ev_in[c], s->s_in);
             }
       }
+      // y pieces that have landed in the bounce buffer are copied out between two uploads, so the
+      // host thread serves both directions while the copy engines and the kernels run
+      size_t drained = 0;
+      auto drain_ready = [&](bool block) {
+            while (drained < downs.size() && downs[drained].ev >= 0) {
+                  cudaError_t q = block ? cudaEventSynchronize(s->ev_out[downs[drained].ev])
+                                        : cudaEventQuery(s->ev_out[downs[drained].ev]);
+                  if (q != cudaSuccess) {
+                        if (q == cudaErrorNotReady)
+                              cudaGetLastError();
+                        return;
+                  }
+                  parallel_copy(y + downs[drained].a, s->sy + downs[drained].a,
+                                (size_t)(downs[drained].b - downs[drained].a) * 8);
+                  ++drained;
+            }
+      };
       // 2. with a bounce buffer the uploads are interleaved with the queueing of the units: a
       //    unit can only be queued after its ev_in has been recorded
       for (int c = 0; c < n && !rc; ++c) {
+            if (bounce_y && !drain)
+                  drain = drain_ready;
+            if (bounce_y)
+                  drain_ready(false);
             if (bounce_x) {
                   if (x_hi[c] > lo)
                         upload_range(lo, x_hi[c]);
@@ -190,17 +216,10 @@ double host_pass(long long N, long long M, const double *x, double *y, int n,
             }
       }
       cudaEventRecord(s->t1, s->s_cmp);
-      // 3. drain the bounce buffer of y piece by piece while later pieces are still in flight
-      size_t late = downs.size();
-      for (size_t i = 0; i < downs.size() && !rc; ++i) {
-            if (downs[i].ev < 0) {
-                  late = i;
-                  break;
-            }
-            if (cudaEventSynchronize(s->ev_out[downs[i].ev]) != cudaSuccess)
-                  break;
-            parallel_copy(y + downs[i].a, s->sy + downs[i].a, (size_t)(downs[i].b - downs[i].a) * 8);
-      }
+      // 3. drain the rest of the bounce buffer piece by piece while later pieces are in flight
+      if (!rc)
+            drain_ready(true);
+      const size_t late = drained;
       cudaError_t e1 = cudaStreamSynchronize(s->s_cmp), e2 = cudaStreamSynchronize(s->s_out),
                   e3 = cudaStreamSynchronize(s->s_in);
       if (rc)

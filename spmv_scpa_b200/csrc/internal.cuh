@@ -41,7 +41,8 @@ struct Knobs {
       int sell = -1;           // -1 auto, 0 never, 1 always route ids 2/4 (CSR) and 2 (HLL) to SELL-P
       int sell_panels = 0;     // 0: by size of x
       int sell_sigma = 16384;  // rows per sorting window
-      int sell_panel_mb = 32;  // target size of a panel's x slice
+      int sell_panel_mb = 64;  // target size of a panel's x slice (C3 sweep: 64 MB beats 43 / 32 MB)
+      int sell_unroll = 4;     // slot columns a lane keeps in flight (4 or 8)
       int sell_max_row = 4096; // longer rows go to the CSR long-row kernels
       int cache = 1;           // entry-point matrix cache: 0 off, 1 full content hash, 2 trust pointers
       int warmup = 1, reps = 3;

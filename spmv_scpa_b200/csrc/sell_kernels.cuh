@@ -31,7 +31,7 @@ namespace b200 {
 
 // One warp per slice, lane = row (the mapping of hll_warp_kernel<1>, which measured best
 // whenever the gather is the limiter).  Slices [slice0, slice0 + n) of one panel.
-template <int EPI>
+template <int EPI, int U>
 __global__ void __launch_bounds__(1024)
     sell_kernel(const long long *__restrict__ soff, const int *__restrict__ perm,
                 const int *__restrict__ ja, const double *__restrict__ as, long long n_slices,
@@ -50,7 +50,6 @@ __global__ void __launch_bounds__(1024)
       const double *sas = as + base;
       const int *sja = ja + base;
 
-      constexpr int U = 4;
       double acc0 = 0.0, acc1 = 0.0;
       for (int j = 0; j < width; j += U) {
             double a[U], xv[U];

@@ -619,15 +619,22 @@ int sell_run(const SellPlan &sp, int wpb, const double *d_x, double *d_y, int ep
       for (int p = 0; p < sp.K; ++p) {
             const long long *soff = sp.d_soff + (size_t)p * (sp.n_slices + 1);
             const int *perm = sp.d_perm + (size_t)p * sp.n_slices * 32;
-            if (p > 0)
-                  sell_kernel<EPI_ACC><<<grid, threads, 0, st>>>(soff, perm, sp.d_ja, sp.d_as,
-                                                                 sp.n_slices, d_x, d_y, epi);
+            const bool u8 = g_knobs.sell_unroll == 8;
+            if (p > 0 && u8)
+                  sell_kernel<EPI_ACC, 8><<<grid, threads, 0, st>>>(soff, perm, sp.d_ja, sp.d_as,
+                                                                    sp.n_slices, d_x, d_y, epi);
+            else if (p > 0)
+                  sell_kernel<EPI_ACC, 4><<<grid, threads, 0, st>>>(soff, perm, sp.d_ja, sp.d_as,
+                                                                    sp.n_slices, d_x, d_y, epi);
             else if (epi_mode == EPI_FUSED)
-                  sell_kernel<EPI_FUSED><<<grid, threads, 0, st>>>(soff, perm, sp.d_ja, sp.d_as,
-                                                                   sp.n_slices, d_x, d_y, epi);
+                  sell_kernel<EPI_FUSED, 4><<<grid, threads, 0, st>>>(soff, perm, sp.d_ja, sp.d_as,
+                                                                      sp.n_slices, d_x, d_y, epi);
+            else if (u8)
+                  sell_kernel<EPI_PLAIN, 8><<<grid, threads, 0, st>>>(soff, perm, sp.d_ja, sp.d_as,
+                                                                      sp.n_slices, d_x, d_y, epi);
             else
-                  sell_kernel<EPI_PLAIN><<<grid, threads, 0, st>>>(soff, perm, sp.d_ja, sp.d_as,
-                                                                   sp.n_slices, d_x, d_y, epi);
+                  sell_kernel<EPI_PLAIN, 4><<<grid, threads, 0, st>>>(soff, perm, sp.d_ja, sp.d_as,
+                                                                      sp.n_slices, d_x, d_y, epi);
             ++g_counters.launches;
       }
       return 0;
@@ -1783,6 +1790,7 @@ extern "C" int spmv_b200_set_knob(const char *key, int value) {
                    {"sell_panels", &g_knobs.sell_panels},
                    {"sell_sigma", &g_knobs.sell_sigma},
                    {"sell_panel_mb", &g_knobs.sell_panel_mb},
+                   {"sell_unroll", &g_knobs.sell_unroll},
                    {"sell_max_row", &g_knobs.sell_max_row},
                    {"cache", &g_knobs.cache}};
       for (auto &t : table)

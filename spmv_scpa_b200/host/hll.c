@@ -12,9 +12,13 @@
  * posix_memalign calls per hack, all JA arrays live in one slab and all AS
  * arrays in another, each hack starting on a 64-byte boundary inside its
  * slab (so every blk->JA / blk->AS keeps the reference's alignment
- * guarantee).  blocks[0].JA / blocks[0].AS are the slab bases.  A 16M-row
- * matrix is then two allocations instead of one million, and the GPU upload
- * can stream the slabs.  Packing runs in parallel over hacks.
+ * guarantee).  A 16M-row matrix is then two allocations instead of one
+ * million, and the GPU upload can stream the slabs.  Packing runs in parallel
+ * over hacks.  Which sparse_hll objects own slabs is kept in a process-local
+ * registry (the struct itself is ABI and has no spare field), so hll_free()
+ * also releases an HLL that was built the reference's way -- one allocation
+ * per hack, src/hll.c:60-61 -- correctly; an HLL built HERE must be released
+ * by THIS hll_free.
  */
 #include <errno.h>
 #include <stdint.h>
@@ -36,6 +40,49 @@
 
 static inline size_t round_up(size_t v, size_t to) {
       return (v + to - 1) / to * to;
+}
+
+/* ---- registry of slab-backed objects: H -> (slab_ja, slab_as) ---------- */
+struct slab_owner {
+      const sparse_hll *H;
+      int *ja;
+      double *as;
+};
+static struct slab_owner *g_owners;
+static size_t g_n_owners, g_cap_owners;
+
+static int owners_add(const sparse_hll *H, int *ja, double *as) {
+      int rc = 0;
+#pragma omp critical(spmv_hll_owners)
+      {
+            if (g_n_owners == g_cap_owners) {
+                  const size_t cap = g_cap_owners ? 2 * g_cap_owners : 16;
+                  struct slab_owner *p = realloc(g_owners, cap * sizeof *p);
+                  if (p)
+                        g_owners = p, g_cap_owners = cap;
+                  else
+                        rc = -ENOMEM;
+            }
+            if (!rc)
+                  g_owners[g_n_owners++] = (struct slab_owner){H, ja, as};
+      }
+      return rc;
+}
+
+/* 1 and the slab bases if H was built by csr_to_hll() below (entry removed) */
+static int owners_take(const sparse_hll *H, int **ja, double **as) {
+      int found = 0;
+#pragma omp critical(spmv_hll_owners)
+      {
+            for (size_t i = 0; i < g_n_owners; ++i)
+                  if (g_owners[i].H == H) {
+                        *ja = g_owners[i].ja, *as = g_owners[i].as;
+                        g_owners[i] = g_owners[--g_n_owners];
+                        found = 1;
+                        break;
+                  }
+      }
+      return found;
 }
 
 sparse_hll *csr_to_hll(const sparse_csr *A, bool is_col_major) {
@@ -75,7 +122,7 @@ sparse_hll *csr_to_hll(const sparse_csr *A, bool is_col_major) {
       int *slab_ja = aligned_malloc((off_ja[nb] + SLAB_ALIGN_JA) * sizeof(int));
       double *slab_as =
           aligned_malloc((off_as[nb] + SLAB_ALIGN_AS) * sizeof(double));
-      if (!slab_ja || !slab_as) {
+      if (!slab_ja || !slab_as || owners_add(H, slab_ja, slab_as)) {
             free(slab_ja);
             free(slab_as);
             goto nomem;
@@ -137,9 +184,18 @@ nomem:
 void hll_free(sparse_hll *H) {
       if (!H)
             return;
-      if (H->blocks && H->num_blocks > 0) {
-            free(H->blocks[0].JA); /* slab bases */
-            free(H->blocks[0].AS);
+      int *slab_ja = NULL;
+      double *slab_as = NULL;
+      if (owners_take(H, &slab_ja, &slab_as)) {
+            free(slab_ja);
+            free(slab_as);
+      } else if (H->blocks) {
+            /* built elsewhere with one allocation per hack (reference src/hll.c:60-61,
+             * released per hack in src/hll.c:97-106) */
+            for (int b = 0; b < H->num_blocks; ++b) {
+                  free(H->blocks[b].JA);
+                  free(H->blocks[b].AS);
+            }
       }
       free(H->blocks);
       free(H);

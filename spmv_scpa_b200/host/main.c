@@ -16,7 +16,13 @@
  *   - OpenMP team sizes larger than the machine are run oversubscribed
  *     instead of aborting on an assert (src/csr.c:320, src/hll.c:184);
  *   - SPMV_B200_SKIP_CPU=1 in the environment skips the serial/OpenMP rows
- *     (useful for the multi-GB synthetic inputs; -d then has no effect).
+ *     (useful for the multi-GB synthetic inputs; -d then has no effect);
+ *   - SPMV_B200_GPUS=N (environment, so scripts/results.py keeps working
+ *     unmodified) adds the row-partitioned iterated SpMV x_{k+1} = A x_k on N
+ *     GPUs after the reference schedule (square matrices; SPMV_B200_STEPS
+ *     steps, default 10) and appends one row to <out-dir>/b200_dist.csv --
+ *     a separate file, the three reference CSVs keep their schema.  With -d
+ *     the first step is validated against the serial CSR result.
  */
 #include <errno.h>
 #include <getopt.h>
@@ -30,6 +36,7 @@
 #include "err.h"
 #include "hll.h"
 #include "logger.h"
+#include "spmv_b200.h"
 #include "utils.h"
 
 static const int k_omp_threads[] = {2, 4, 8, 16, 32, 40};
@@ -188,6 +195,62 @@ static void run_hll_cuda(void) {
       }
 }
 
+/* Multi-GPU iterated SpMV through the C ABI (include/spmv_b200.h, csrc/dist.cu). */
+static void run_multi_gpu(const char *out_dir, int gpus) {
+      const char *env = getenv("SPMV_B200_STEPS");
+      const int steps = env && atoi(env) > 0 ? atoi(env) : 10;
+      if (g.A->M != g.A->N) {
+            LOG_ERR("SPMV_B200_GPUS: x_{k+1} = A x_k needs a square matrix, skipped");
+            return;
+      }
+      spmv_b200_dist_group *grp = spmv_b200_dist_group_create(
+          g.A, gpus, SPMV_B200_CSR_ADAPTIVE, 4, SPMV_B200_DIST_AUTO);
+      if (!grp) {
+            LOG_ERR("multi-GPU setup failed: %s", spmv_b200_last_error());
+            die();
+      }
+      vec y = vec_create((size_t)g.A->M);
+      double ms = 0.0;
+      int rc = y.data ? 0 : -ENOMEM;
+      /* one step first: y = A x, comparable with the serial CSR result */
+      rc = rc ? rc : spmv_b200_dist_group_set_x(grp, g.x.data);
+      rc = rc ? rc : spmv_b200_dist_group_iterate(grp, 1, NULL);
+      rc = rc ? rc : spmv_b200_dist_group_get_x(grp, y.data);
+      if (!rc && g.debug && g.expected.data &&
+          validation_vec_result(g.expected, y) != 0) {
+            LOG_ERR("[multi-GPU CSR, %d GPUs] validation failed", gpus);
+            rc = -EIO;
+      }
+      /* then the timed iteration (warm: plans and the CUDA graph exist) */
+      rc = rc ? rc : spmv_b200_dist_group_set_x(grp, g.x.data);
+      rc = rc ? rc : spmv_b200_dist_group_iterate(grp, 4, NULL);
+      rc = rc ? rc : spmv_b200_dist_group_iterate(grp, steps, &ms);
+      if (rc) {
+            LOG_ERR("multi-GPU run failed: %s", spmv_b200_last_error());
+            vec_put(&y);
+            spmv_b200_dist_group_destroy(grp);
+            die();
+      }
+      char path[MAX_PATH];
+      snprintf(path, sizeof path, "%s/b200_dist.csv", out_dir);
+      FILE *probe = fopen(path, "r");
+      FILE *f = fopen(path, "a");
+      if (f) {
+            if (!probe)
+                  fprintf(f, "matrix,gpus,exchange,steps,rows,cols,nnz,ms_per_step,gflops\n");
+            const int push = spmv_b200_dist_mode(spmv_b200_dist_group_rank(grp, 0)) ==
+                             SPMV_B200_DIST_PUSH;
+            fprintf(f, "%s,%d,%s,%d,%d,%d,%d,%f,%f\n", g.A->name, gpus,
+                    push ? "push" : "nccl", steps, g.A->M, g.A->N, g.A->NZ, ms / steps,
+                    compute_gflops(ms / steps, g.A->NZ));
+            fclose(f);
+      }
+      if (probe)
+            fclose(probe);
+      vec_put(&y);
+      spmv_b200_dist_group_destroy(grp);
+}
+
 int main(int argc, char **argv) {
       static const struct option long_opts[] = {
           {"matrix", required_argument, NULL, 'm'},
@@ -259,6 +322,9 @@ int main(int argc, char **argv) {
       }
       run_csr_cuda();
       run_hll_cuda();
+      const char *gpus = getenv("SPMV_B200_GPUS");
+      if (gpus && atoi(gpus) >= 1)
+            run_multi_gpu(out_dir, atoi(gpus));
 
       teardown();
       return EXIT_SUCCESS;

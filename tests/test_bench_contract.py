@@ -18,7 +18,7 @@ def run_bench(*args):
                        text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
-    assert len(lines) == 1, lines
+    assert len(lines) == 1, lines          # ONE line on stdout, whatever the libraries print
     return json.loads(lines[0])
 
 

@@ -115,3 +115,24 @@ def test_reference_driver_runs_on_libspmv_b200(tmp_path):
     key = lambda l: l.split(",")[:8]
     assert [key(l) for l in read(out2, "cuda.csv")] == [key(l) for l in c]
     assert [l.split(",")[:6] for l in read(out2, "serial.csv")] == [l.split(",")[:6] for l in read(out, "serial.csv")]
+
+
+@pytest.mark.gpu
+def test_multi_gpu_rows_from_the_cli(tmp_path):
+    """SPMV_B200_GPUS=N: the iterated SpMV runs behind the C ABI from the C driver (no Python in
+    the loop), is validated by -d against the serial CSR result, and logs to its own CSV."""
+    import spmv_scpa_b200 as sp
+    n = min(sp._lib.b200.spmv_b200_device_count(), 2)
+    A = sp.gen_stencil27(20, 18, 16)
+    mtx = str(tmp_path / "stencil.mtx")
+    sp.gen_write_mtx(A, mtx)
+    out = str(tmp_path)
+    env = dict(os.environ, SPMV_B200_GPUS=str(n), SPMV_B200_STEPS="6", SPMV_B200_SKIP_CPU="0")
+    r = subprocess.run([SPMV, "-m", mtx, "-o", out, "-d"], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr
+    rows = read(out, "b200_dist.csv")
+    assert rows[0] == "matrix,gpus,exchange,steps,rows,cols,nnz,ms_per_step,gflops" and len(rows) == 2
+    f = rows[1].split(",")
+    assert f[0] == "stencil" and int(f[1]) == n and f[2] in ("push", "nccl") and int(f[3]) == 6
+    assert (int(f[4]), int(f[6])) == (A.M, A.NZ) and float(f[7]) > 0
+    assert len(read(out, "cuda.csv")) == 28          # the reference schedule is untouched

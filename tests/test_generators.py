@@ -78,3 +78,22 @@ def test_ragged_covers_all_bins(sp, tmp_path):
 def test_too_large_is_refused(sp):
     with pytest.raises(MemoryError):
         sp.gen_stencil27(512, 512, 512)             # nnz > INT_MAX: not representable as sparse_csr
+
+
+def test_oracle_side_generators_equal_the_product_generators(sp, O):
+    """bench.py --impl reference builds its inputs with the generators restated in oracle/oracle.c
+    (it must not map a product library): both sides produce identical arrays."""
+    pairs = [(lambda: O.gen_stencil27(7, 5, 6), lambda: sp.gen_stencil27(7, 5, 6)),
+             (lambda: O.gen_stencil27_rows(9, 4, 8, 72, 180), lambda: sp.gen_stencil27_rows(9, 4, 8, 72, 180)),
+             (lambda: O.gen_poisson2d(13, 7), lambda: sp.gen_poisson2d(13, 7)),
+             (lambda: O.gen_uniform_rows(900, 9, 42, 0, 900), lambda: sp.gen_uniform_random(900, 9, 42)),
+             (lambda: O.gen_rmat(10, 8), lambda: sp.gen_rmat(10, 8))]
+    for mk_o, mk_p in pairs:
+        M, N, IRP, JA, AS = mk_o()
+        A = mk_p()
+        assert (M, N) == (A.M, A.N)
+        assert np.array_equal(IRP, A.IRP) and np.array_equal(JA, A.JA) and np.array_equal(AS, A.AS)
+    # a row range of the uniform matrix regenerates independently
+    M, N, IRP, JA, AS = O.gen_uniform_rows(900, 9, 42, 300, 500)
+    A = sp.gen_uniform_random(900, 9, 42)
+    assert np.array_equal(JA, A.JA[300 * 9:500 * 9]) and np.array_equal(AS, A.AS[300 * 9:500 * 9])

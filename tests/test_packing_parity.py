@@ -279,3 +279,51 @@ def test_loader_and_packer_properties(sp, O, tmp_path, text):
                 got += ln
             assert got == nzb
             assert w == max([A.IRP[32 * b + i + 1] - A.IRP[32 * b + i] for i in range(m)] + [0])
+
+
+def test_hll_free_handles_both_ownership_layouts(sp, O):
+    """hll_free() releases an HLL built here (two slabs) and one built the reference's way (one
+    allocation per hack, src/hll.c:60-61) -- valgrind-free by construction: run both in a loop
+    and watch the resident set."""
+    import ctypes as C
+    import resource
+    L = sp._lib.host
+    libc = C.CDLL(None)
+    libc.malloc.restype = C.c_void_p
+    libc.malloc.argtypes = [C.c_size_t]
+    A = sp.gen_stencil27(20, 20, 20)
+    S = sp.structs
+
+    def build_reference_style():
+        """per-hack allocations through the C allocator, as the reference packer does"""
+        src = sp.csr_to_hll(A, True)
+        nb = src.num_blocks
+        H = C.cast(libc.malloc(C.sizeof(S.sparse_hll)), C.POINTER(S.sparse_hll))
+        C.memmove(H, src.ptr, C.sizeof(S.sparse_hll))
+        blocks = C.cast(libc.malloc(nb * C.sizeof(S.ellpack_block)), C.POINTER(S.ellpack_block))
+        for b in range(nb):
+            blk = src.struct.blocks[b]
+            n = blk.M * blk.max_NZ
+            ja = C.cast(libc.malloc(max(n, 1) * 4), C.POINTER(C.c_int))
+            as_ = C.cast(libc.malloc(max(n, 1) * 8), C.POINTER(C.c_double))
+            C.memmove(ja, blk.JA, n * 4)
+            C.memmove(as_, blk.AS, n * 8)
+            blocks[b] = S.ellpack_block(blk.M, blk.N, blk.NZ, blk.max_NZ, ja, as_)
+        H.contents.blocks = blocks
+        src.free()
+        return H
+
+    def rss_mb():
+        return resource.getrusage(resource.RUSAGE_SELF).ru_maxrss / 1024.0
+
+    for _ in range(3):
+        L.hll_free(C.cast(build_reference_style(), C.c_void_p))
+        sp.csr_to_hll(A, False).free()
+    base = rss_mb()
+    for _ in range(40):                                  # 40 x ~3.5 MB would show as > 100 MB
+        L.hll_free(C.cast(build_reference_style(), C.c_void_p))
+        sp.csr_to_hll(A, False).free()
+    assert rss_mb() - base < 40.0
+    # an empty matrix still owns (and releases) its slabs
+    E = sp.csr_from_arrays("empty", 0, 5, np.zeros(1, np.int32), np.zeros(0, np.int32), np.zeros(0))
+    sp.csr_to_hll(E, True).free()

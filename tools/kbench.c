@@ -25,6 +25,7 @@
 
 static int g_reps = 20, g_warmup = 3, g_flush = 0, g_quick = 0, g_profile = 0, g_cfg_from = -1;
 static int g_sell = 0;
+static int g_panels[16] = {1, 2, 3, 4, 6, 8, 16}, g_n_panels = 7;
 static double g_peak = 6559.7; /* MEASURED_PEAKS.json hbm_gbs of this pool */
 static const char *g_only = "";
 
@@ -154,6 +155,11 @@ int main(int argc, char **argv) {
                   g_profile = 1; /* only the headline kernels: for ncu captures */
             else if (!strcmp(argv[i], "--sell"))
                   g_sell = 1; /* SELL-P sweep: panels x sigma x warps/block, CSR and HLL source */
+            else if (!strcmp(argv[i], "--panels") && i + 1 < argc) {
+                  g_n_panels = 0;
+                  for (char *tok = strtok(argv[++i], ","); tok && g_n_panels < 16; tok = strtok(NULL, ","))
+                        g_panels[g_n_panels++] = atoi(tok);
+            }
       }
       spmv_b200_devinfo info;
       if (spmv_b200_device_info(&info)) {
@@ -203,7 +209,7 @@ int main(int argc, char **argv) {
       char knob[64];
 
       if (g_sell) {
-            static const int panels[] = {1, 2, 3, 4, 6, 8, 16};
+            const int *panels = g_panels;
             static const int sigmas[] = {1024, 16384, 262144};
             int64_t info[8];
             /* what the library picks on its own, then the old paths, then the sweep */
@@ -225,7 +231,7 @@ int main(int argc, char **argv) {
             run_csr(&c, h, 4, 4, "sell=0");
             spmv_b200_csr_destroy(h);
             spmv_b200_set_knob("sell", 1);
-            for (int ip = 0; ip < 7; ++ip) {
+            for (int ip = 0; ip < g_n_panels; ++ip) {
                   for (int is = 0; is < 3; ++is) {
                         if (is != 1 && !(panels[ip] == 1 || panels[ip] == 4))
                               continue; /* sigma only matters for padding: sweep it at two panel counts */
@@ -249,7 +255,7 @@ int main(int argc, char **argv) {
             if (strcmp(g_only, "csr")) {
                   spmv_b200_set_knob("sell_sigma", 16384);
                   spmv_b200_csr *hc = spmv_b200_csr_create(A);
-                  for (int ip = -1; ip < 7; ++ip) {
+                  for (int ip = -1; ip < g_n_panels; ++ip) {
                         spmv_b200_set_knob("sell", ip < 0 ? 0 : 1);
                         spmv_b200_set_knob("sell_panels", ip < 0 ? 0 : panels[ip]);
                         spmv_b200_hll *hh = hc ? spmv_b200_hll_from_csr(hc) : NULL;
