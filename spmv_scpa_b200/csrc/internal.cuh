@@ -128,7 +128,8 @@ struct SellPlan {
       int *d_perm = nullptr;
       int *d_ja = nullptr;
       double *d_as = nullptr;
-      // rows too long for a slice (CSR source only): CTA-per-row and split lists
+      // rows too long for a slice (CSR source only): warp-per-row, CTA-per-row and split lists
+      RowList long_warp;
       RowList long_block;
       SplitPlan long_split;
       long long n_long = 0;

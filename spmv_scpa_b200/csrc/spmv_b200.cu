@@ -89,6 +89,7 @@ void free_split(SplitPlan &s) {
 }
 void free_sell(SellPlan &sp) {
       cudaFree(sp.d_soff), cudaFree(sp.d_perm), cudaFree(sp.d_ja), cudaFree(sp.d_as);
+      free_list(sp.long_warp);
       free_list(sp.long_block);
       free_split(sp.long_split);
       sp = SellPlan();
@@ -656,7 +657,11 @@ bool csr_wants_sell(spmv_b200_csr *h) {
 int csr_ensure_sell(spmv_b200_csr *h) {
       if (h->sell.state != 0)
             return h->sell.state == 1 ? 0 : -1;
-      const int K = sell_panels_for(h->N, h->gather_span);
+      // Ragged / power-law rows take ONE panel whatever the size of x: their columns are as
+      // skewed as their rows (R-MAT: a few hot columns serve most gathers), panels measured no
+      // gain there and cost a pass over y and the row order each (profiles/r2_kbench_c4_sell.txt).
+      const bool ragged = !h->segs.empty() && !h->segs[0].regular;
+      const int K = ragged && g_knobs.sell_panels <= 0 ? 1 : sell_panels_for(h->N, h->gather_span);
       std::vector<int> long_rows;
       int rc;
       if (h->wide)
@@ -667,13 +672,18 @@ int csr_ensure_sell(spmv_b200_csr *h) {
                             g_knobs.sell_max_row, h->sell, &long_rows);
       if (rc || h->sell.state != 1)
             return -1;
-      // rows too long for a slice: CTA per row up to 65 536 entries, split beyond
-      std::vector<int> blk, spl;
-      for (int r : long_rows)
-            (h->h_irp[r + 1] - h->h_irp[r] <= kKindMax[6] ? blk : spl).push_back(r);
+      // rows too long for a slice: a warp per row up to 2048 entries, a CTA per row up to 65 536,
+      // split into chunks beyond (the bins of the direct path)
+      std::vector<int> wrp, blk, spl;
+      for (int r : long_rows) {
+            const long long len = h->h_irp[r + 1] - h->h_irp[r];
+            (len <= kKindMax[5] ? wrp : (len <= kKindMax[6] ? blk : spl)).push_back(r);
+      }
       h->sell.n_long = (long long)long_rows.size();
+      h->sell.long_warp.n = (long long)wrp.size();
       h->sell.long_block.n = (long long)blk.size();
-      if (upload(&h->sell.long_block.d_rows, blk) || build_split(h, spl, h->sell.long_split)) {
+      if (upload(&h->sell.long_warp.d_rows, wrp) || upload(&h->sell.long_block.d_rows, blk) ||
+          build_split(h, spl, h->sell.long_split)) {
             free_sell(h->sell);
             h->sell.state = -1;
             return -1;
@@ -783,10 +793,15 @@ int csr_run(spmv_b200_csr *h, int kernel, int wpb, long long row0, long long row
             }
             sell_run(sp, wpb, d_x, d_y, epi_mode, epi, st);
             CsrArgs a{h, d_x, d_y, EPI_PLAIN, EpiArgs{}, st, 512};
-            if (h->wide)
+            CsrArgs aw = a;
+            aw.threads = 256;
+            if (h->wide) {
+                  launch_vec<long long>(aw, 5, 0, sp.long_warp.n, sp.long_warp.d_rows, -1);
                   launch_block_rows<long long>(a, 0, sp.long_block.n, sp.long_block.d_rows);
-            else
+            } else {
+                  launch_vec<int>(aw, 5, 0, sp.long_warp.n, sp.long_warp.d_rows, -1);
                   launch_block_rows<int>(a, 0, sp.long_block.n, sp.long_block.d_rows);
+            }
             launch_split(a, sp.long_split);
       } else {
             if (want_dot) {
@@ -1169,7 +1184,8 @@ extern "C" int spmv_b200_csr_launches(const spmv_b200_csr *h, int kernel) {
             return -EINVAL;
       const bool sell_id = kernel == SPMV_B200_CSR_ADAPTIVE || kernel == SPMV_B200_CSR_STREAM;
       if (sell_id && h->sell.state == 1 && csr_wants_sell(const_cast<spmv_b200_csr *>(h)))
-            return h->sell.K + (h->sell.long_block.n > 0) + (h->sell.long_split.n_rows ? 2 : 0);
+            return h->sell.K + (h->sell.long_warp.n > 0) + (h->sell.long_block.n > 0) +
+                   (h->sell.long_split.n_rows ? 2 : 0);
       int n = 0;
       for (auto &sg : h->segs) {
             if (sg.r1 == sg.r0)
