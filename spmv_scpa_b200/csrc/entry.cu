@@ -12,6 +12,7 @@
 #include "internal.cuh"
 
 #include <omp.h>
+#include <unistd.h>
 
 #include <functional>
 
@@ -91,15 +92,33 @@ bool is_pinned(const void *p) {
       return at.type == cudaMemoryTypeHost;
 }
 
-// memcpy spread over the OpenMP team (pageable <-> bounce buffer)
+// Threads for the bounce-buffer copies: an explicit team size, because launchers such as
+// torchrun export OMP_NUM_THREADS=1 to every rank (a num_threads clause overrides the variable);
+// the host's cores are shared between the ranks of one box (LOCAL_WORLD_SIZE).
+int copy_threads() {
+      static int n = 0;
+      if (!n) {
+            long cores = sysconf(_SC_NPROCESSORS_ONLN);
+            const char *lw = getenv("LOCAL_WORLD_SIZE");
+            const long ranks = lw && atoi(lw) > 0 ? atoi(lw) : 1;
+            n = (int)std::max(1l, std::min(16l, cores / ranks));
+            const char *env = getenv("SPMV_B200_COPY_THREADS");
+            if (env && atoi(env) > 0)
+                  n = atoi(env);
+      }
+      return n;
+}
+
+// memcpy spread over an OpenMP team (pageable <-> bounce buffer)
 void parallel_copy(void *dst, const void *src, size_t bytes) {
       constexpr size_t kBlock = 256u << 10; // small enough that an 8 MiB piece feeds every core
       const long long blocks = (long long)((bytes + kBlock - 1) / kBlock);
-      if (blocks <= 2) {
+      const int nt = copy_threads();
+      if (blocks <= 2 || nt == 1) {
             memcpy(dst, src, bytes);
             return;
       }
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(nt)
       for (long long b = 0; b < blocks; ++b) {
             const size_t off = (size_t)b * kBlock;
             memcpy((char *)dst + off, (const char *)src + off, std::min(kBlock, bytes - off));
