@@ -162,8 +162,9 @@ int spmv_b200_csr_spmv_fused(spmv_b200_csr *h, int kernel, int warps_per_block,
 int spmv_b200_csr_spmv_host(spmv_b200_csr *h, int kernel, int warps_per_block, const double *x,
                             double *y, double *kernel_ms);
 /* SELL-P plan of this matrix (column-panelled, window-sorted slices; csrc/sell_kernels.cuh):
- * out[0..8) = {state (1 built), panels, sigma, slices, padded slots, entries in slices, rows
- * handled by the long-row kernels, gather span * 1e6}.  build != 0 builds the plan first. */
+ * out[0..11) = {state (1 built), panels, sigma, slices, padded slots, entries in slices, rows
+ * handled by the long-row kernels, gather span * 1e6, virtual-row chunk (0: none), rows split into
+ * pieces, pieces}.  build != 0 builds the plan first. */
 int spmv_b200_csr_sell_info(spmv_b200_csr *h, int build, int64_t *out, int n_out);
 /* Device SELL-P arrays back to the host for bit-compare (any output may be NULL):
  * soff[panels*(slices+1)], perm[panels*slices*32], JA/AS[slots]. */
@@ -172,6 +173,11 @@ int spmv_b200_csr_sell_download(const spmv_b200_csr *h, int64_t *soff, int *perm
 /* Host half of the SELL-P build (row order and slice offsets from per-panel row counts,
  * counts[p*M + r], -1 = row excluded); needs no GPU.  perm[K*S*32], soff[K*(S+1)], S = ceil(M/32). */
 int spmv_b200_sell_plan(const int *counts, int64_t M, int K, int sigma, int *perm, int64_t *soff);
+/* Host half of the virtual-row form (ragged matrices): sizes[4] = {virtual rows, slices, rows
+ * split into pieces, pieces}; dest[slices*32] (row, -1, or -2-piece) and soff[slices+1] may be
+ * NULL on a first call that only asks for the sizes.  `irp`: M+1 64-bit offsets.  No GPU. */
+int spmv_b200_sell_plan_vrows(const int64_t *irp, int64_t M, int chunk, int sigma, int64_t *sizes,
+                              int *dest, int64_t *soff);
 /* Kernel launches one spmv call issues for this matrix/kernel. */
 int spmv_b200_csr_launches(const spmv_b200_csr *h, int kernel);
 /* Run `warmup` untimed + `reps` timed launches, each bracketed by CUDA events
@@ -240,7 +246,7 @@ void spmv_b200_counters(int64_t *launches, int64_t *h2d_bytes,
 
 /* Experiment knobs used by bin/kbench sweeps and tests ("csr_stream_cfg", "hll_vec",
  * "hll_stream_cfg", "regular_lpr", "adaptive_direct", "force_wide", "pipeline", "pipe_chunks",
- * "sell", "sell_panels", "sell_sigma", "sell_panel_mb", "sell_max_row", "sell_unroll", "cache",
+ * "sell", "sell_panels", "sell_sigma", "sell_panel_mb", "sell_max_row", "sell_unroll", "sell_chunk", "cache",
  * "l2_fetch_granularity").  0 or -EINVAL.  Knobs that change planning must be set before a
  * handle is created. */
 int spmv_b200_set_knob(const char *key, int value);

@@ -224,6 +224,57 @@ def sellp_layout(M, N, IRP, JA, AS, K, sigma, max_row):
     return soff, perm, ja, as_
 
 
+def sellv_layout(M, IRP, JA, AS, sigma, chunk):
+    """SELL-P with virtual rows (one panel; sell_kernels.cuh): every row longer than `chunk` entries is
+    cut into pieces of at most `chunk` entries, in order; the pieces ("virtual rows", numbered row by
+    row) are ordered inside windows of `sigma` virtual rows by length, descending, ties by number;
+    a lane's destination is the row (unsplit), or -2-i for piece i of the split rows (pieces numbered
+    in row order), or -1.  Returns soff[1, S+1], dest[1, S*32], ja, as, split_row, split_first."""
+    IRP = np.asarray(IRP, np.int64)
+    JA = np.asarray(JA, np.int64)
+    AS = np.asarray(AS, np.float64)
+    pieces = []            # (first entry, length, destination)
+    split_row, split_first, p = [], [], 0
+    for r in range(M):
+        L = int(IRP[r + 1] - IRP[r])
+        if L <= chunk:
+            pieces.append((int(IRP[r]), L, r))
+            continue
+        split_row.append(r)
+        split_first.append(p)
+        for j0 in range(0, L, chunk):
+            pieces.append((int(IRP[r]) + j0, min(chunk, L - j0), -2 - p))
+            p += 1
+    split_first.append(p)
+    V = len(pieces)
+    S = (V + 31) // 32
+    order = np.full(S * 32, -1, np.int64)
+    for w0 in range(0, V, sigma):
+        w1 = min(V, w0 + sigma)
+        vs = sorted(range(w0, w1), key=lambda v: (-pieces[v][1], v))
+        order[w0:w0 + len(vs)] = vs
+    width = np.array([pieces[order[s * 32]][1] if order[s * 32] >= 0 else 0 for s in range(S)], np.int64)
+    soff = np.zeros((1, S + 1), np.int64)
+    soff[0, 1:] = np.cumsum(32 * width)
+    dest = np.full((1, S * 32), -1, np.int32)
+    ja = np.zeros(soff[0, -1], np.int32)
+    as_ = np.zeros(soff[0, -1], np.float64)
+    for s in range(S):
+        w = int(width[s])
+        bj = ja[soff[0, s]:soff[0, s + 1]].reshape(w, 32)
+        ba = as_[soff[0, s]:soff[0, s + 1]].reshape(w, 32)
+        for i in range(32):
+            v = order[s * 32 + i]
+            if v < 0:
+                continue
+            k0, n, d = pieces[v]
+            dest[0, s * 32 + i] = d
+            bj[:n, i] = JA[k0:k0 + n]
+            ba[:n, i] = AS[k0:k0 + n]
+            bj[n:, i] = JA[k0 + n - 1] if n else 0
+    return soff, dest, ja, as_, np.array(split_row, np.int32), np.array(split_first, np.int32)
+
+
 def csr_spmv(M, IRP, JA, AS, x):
     """y = A x, strict left-to-right FP64 (reference src/csr.c:201-216)."""
     IRP = np.ascontiguousarray(IRP)

@@ -43,7 +43,8 @@ struct Knobs {
       int sell_sigma = 16384;  // rows per sorting window
       int sell_panel_mb = 64;  // target size of a panel's x slice (C3 sweep: 64 MB beats 43 / 32 MB)
       int sell_unroll = 4;     // slot columns a lane keeps in flight (4 or 8)
-      int sell_max_row = 4096; // longer rows go to the CSR long-row kernels
+      int sell_max_row = 4096; // longer rows go to the CSR long-row kernels (panel mode)
+      int sell_chunk = 64;     // ragged matrices: rows are cut into virtual rows of this many entries; 0 = off
       int cache = 1;           // entry-point matrix cache: 0 off, 1 full content hash, 2 trust pointers
       int warmup = 1, reps = 3;
 };
@@ -128,6 +129,12 @@ struct SellPlan {
       int *d_perm = nullptr;
       int *d_ja = nullptr;
       double *d_as = nullptr;
+      // virtual rows (ragged CSR, one panel): rows longer than `chunk` are cut into pieces whose
+      // partial sums are combined per row; M then counts virtual rows
+      int chunk = 0;
+      long long n_rows = 0, n_split_rows = 0, n_partials = 0;
+      int *d_split_row = nullptr, *d_split_first = nullptr;
+      double *d_partial = nullptr;
       // rows too long for a slice (CSR source only): warp-per-row, CTA-per-row and split lists
       RowList long_warp;
       RowList long_block;

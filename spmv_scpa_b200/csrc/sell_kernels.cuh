@@ -15,6 +15,15 @@
 //     slice have (nearly) equal length and padding disappears even for power-law rows
 //     (BASELINE configs[3]); y is written through the permutation, and stays inside the window.
 //
+//   * virtual rows (one panel only).  A slice is walked by ONE warp, so a 4000-entry row in a
+//     slice is a millisecond of serial latency at the tail of the launch.  For ragged matrices
+//     every row longer than `chunk` entries is cut into virtual rows of at most `chunk` entries;
+//     slices are built over virtual rows, every warp gets at most `chunk` steps, the hub rows
+//     of a power-law matrix spread over thousands of lanes, and no separate long-row kernel is
+//     left.  A virtual row of an unsplit row stores y directly; the pieces of a split row store
+//     partial sums that csr_combine_kernel adds in piece order (deterministic, no atomics).
+//     perm then holds the DESTINATION of a lane: row >= 0, -1 = none, -2-i = partial[i].
+//
 // Layout, per panel p and slice s (S = ceil(M/32) slices in every panel):
 //   soff[p*(S+1) + s]        slot offset of the slice; (soff[..+1] - soff[..]) / 32 = width
 //   perm[(p*S + s)*32 + i]   local row of lane i, or -1 (no row: tail of the last window, or a
@@ -31,11 +40,12 @@ namespace b200 {
 
 // One warp per slice, lane = row (the mapping of hll_warp_kernel<1>, which measured best
 // whenever the gather is the limiter).  Slices [slice0, slice0 + n) of one panel.
-template <int EPI, int U>
+template <int EPI, int U, bool VROWS = false>
 __global__ void __launch_bounds__(1024)
     sell_kernel(const long long *__restrict__ soff, const int *__restrict__ perm,
                 const int *__restrict__ ja, const double *__restrict__ as, long long n_slices,
-                const double *__restrict__ x, double *__restrict__ y, EpiArgs epi) {
+                const double *__restrict__ x, double *__restrict__ y,
+                double *__restrict__ partial, EpiArgs epi) {
       const long long s = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
       if (s >= n_slices)
             return; // whole warp
@@ -75,6 +85,8 @@ __global__ void __launch_bounds__(1024)
       double dot_acc = 0.0;
       if (row >= 0)
             store_y<EPI>(y, row, acc0 + acc1, epi, dot_acc);
+      else if (VROWS && row < -1)
+            partial[-2 - row] = acc0 + acc1; // a piece of a split row
       epi_finish_warp<EPI>(epi, dot_acc, s);
 }
 
@@ -168,6 +180,40 @@ __global__ void sell_fill_kernel(Src src, long long n_slices, PanelBounds pb,
                         last_col = c;
                         break;
                   }
+            }
+            as[base + (long long)out * 32 + lane] = a;
+            ja[base + (long long)out * 32 + lane] = last_col;
+      }
+}
+
+// Virtual-row fill (one panel): lane = virtual row perm_v[...] = entries [j0, j0 + len) of row
+// vr_row[v], len = min(chunk, row length - j0).
+template <typename Src>
+__global__ void sell_fill_vrow_kernel(Src src, long long n_slices, const long long *__restrict__ soff,
+                                      const int *__restrict__ perm_v, const int *__restrict__ vr_row,
+                                      const int *__restrict__ vr_j0, int chunk, int *__restrict__ ja,
+                                      double *__restrict__ as) {
+      const long long s = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+      if (s >= n_slices)
+            return;
+      const int lane = threadIdx.x & 31;
+      const long long base = soff[s];
+      const int width = (int)((soff[s + 1] - base) >> 5);
+      const int v = perm_v[s * 32 + lane];
+      long long row = 0;
+      int j0 = 0, len = 0;
+      if (v >= 0) {
+            row = vr_row[v];
+            j0 = vr_j0[v];
+            len = min(chunk, src.len(row) - j0);
+      }
+      int last_col = 0;
+      for (int out = 0; out < width; ++out) {
+            double a = 0.0;
+            if (out < len) {
+                  const long long k = src.at(row, j0 + out);
+                  a = src.as[k];
+                  last_col = src.ja[k];
             }
             as[base + (long long)out * 32 + lane] = a;
             ja[base + (long long)out * 32 + lane] = last_col;

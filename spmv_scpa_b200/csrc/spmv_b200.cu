@@ -92,6 +92,7 @@ void free_sell(SellPlan &sp) {
       free_list(sp.long_warp);
       free_list(sp.long_block);
       free_split(sp.long_split);
+      cudaFree(sp.d_split_row), cudaFree(sp.d_split_first), cudaFree(sp.d_partial);
       sp = SellPlan();
 }
 void free_segment(Segment &sg) {
@@ -612,30 +613,134 @@ int sell_build(const Src &src, long long M, long long N, int K, int max_row, Sel
       return 0;
 }
 
+// Virtual rows of a ragged CSR (see sell_kernels.cuh): rows longer than `chunk` become
+// ceil(len / chunk) pieces.  vr_row / vr_j0 describe the pieces, dest[v] where a piece stores
+// (row, or -2-i for partial i), split_row / split_first the rows whose partials are combined.
+void sell_virtual_rows(const std::vector<long long> &irp, long long M, int chunk,
+                       std::vector<int> &vr_row, std::vector<int> &vr_j0, std::vector<int> &vr_len,
+                       std::vector<int> &dest, std::vector<int> &split_row,
+                       std::vector<int> &split_first) {
+      long long V = 0, P = 0;
+      for (long long r = 0; r < M; ++r) {
+            const long long len = irp[r + 1] - irp[r];
+            const long long pieces = len > chunk ? (len + chunk - 1) / chunk : 1;
+            V += pieces;
+            P += pieces > 1 ? pieces : 0;
+      }
+      vr_row.resize((size_t)V), vr_j0.resize((size_t)V), vr_len.resize((size_t)V), dest.resize((size_t)V);
+      split_row.clear(), split_first.clear();
+      long long v = 0, p = 0;
+      for (long long r = 0; r < M; ++r) {
+            const long long len = irp[r + 1] - irp[r];
+            if (len <= chunk) {
+                  vr_row[v] = (int)r, vr_j0[v] = 0, vr_len[v] = (int)len, dest[v] = (int)r;
+                  ++v;
+                  continue;
+            }
+            split_row.push_back((int)r);
+            split_first.push_back((int)p);
+            for (long long j0 = 0; j0 < len; j0 += chunk, ++v, ++p) {
+                  vr_row[v] = (int)r, vr_j0[v] = (int)j0;
+                  vr_len[v] = (int)std::min<long long>(chunk, len - j0);
+                  dest[v] = (int)(-2 - p);
+            }
+      }
+      split_first.push_back((int)p);
+}
+
+template <typename Src>
+int sell_build_vrows(const Src &src, const std::vector<long long> &irp, long long M, long long N,
+                     int chunk, SellPlan &sp) {
+      sp.state = -1;
+      if (M <= 0 || irp[M] + M >= (1ll << 31) - 64)
+            return 0;
+      const int sigma = std::max(32, g_knobs.sell_sigma / 32 * 32);
+      std::vector<int> vr_row, vr_j0, vr_len, dest, split_row, split_first;
+      sell_virtual_rows(irp, M, chunk, vr_row, vr_j0, vr_len, dest, split_row, split_first);
+      const long long V = (long long)vr_row.size(), S = (V + 31) / 32;
+      std::vector<int> perm_v;
+      std::vector<long long> soff;
+      sell_plan_host(vr_len, V, 1, sigma, perm_v, soff, &sp.nnz_in_slices, nullptr);
+      std::vector<int> perm_dest(perm_v.size());
+      for (size_t i = 0; i < perm_v.size(); ++i)
+            perm_dest[i] = perm_v[i] >= 0 ? dest[perm_v[i]] : -1;
+      sp.K = 1, sp.sigma = sigma, sp.M = V, sp.n_slices = S, sp.chunk = chunk, sp.n_rows = M;
+      sp.pc = {0, (int)N};
+      sp.slots = soff.back();
+      sp.n_split_rows = (long long)split_row.size();
+      sp.n_partials = split_first.back();
+      int *d_perm_v = nullptr, *d_vr_row = nullptr, *d_vr_j0 = nullptr;
+      int rc = upload(&d_perm_v, perm_v);
+      rc = rc ? rc : upload(&d_vr_row, vr_row);
+      rc = rc ? rc : upload(&d_vr_j0, vr_j0);
+      rc = rc ? rc : upload(&sp.d_perm, perm_dest);
+      rc = rc ? rc : upload(&sp.d_soff, soff);
+      if (!rc && sp.n_split_rows) {
+            rc = upload(&sp.d_split_row, split_row);
+            rc = rc ? rc : upload(&sp.d_split_first, split_first);
+            if (!rc && cudaMalloc(&sp.d_partial, (size_t)sp.n_partials * sizeof(double)) != cudaSuccess)
+                  rc = fail(-ENOMEM, "SELL partial sums: out of device memory");
+      }
+      if (!rc && (cudaMalloc(&sp.d_ja, ((size_t)sp.slots + 32) * sizeof(int)) != cudaSuccess ||
+                  cudaMalloc(&sp.d_as, ((size_t)sp.slots + 32) * sizeof(double)) != cudaSuccess))
+            rc = fail(-ENOMEM, "SELL slices: out of device memory");
+      if (!rc) {
+            sell_fill_vrow_kernel<<<blocks_for(S * 32, 256), 256>>>(src, S, sp.d_soff, d_perm_v, d_vr_row,
+                                                                    d_vr_j0, chunk, sp.d_ja, sp.d_as);
+            g_counters.launches += 1;
+            cudaError_t e = cudaDeviceSynchronize();
+            if (e != cudaSuccess)
+                  rc = fail(-EIO, "SELL fill kernel failed: %s", cudaGetErrorString(e));
+      }
+      cudaFree(d_perm_v), cudaFree(d_vr_row), cudaFree(d_vr_j0);
+      if (rc)
+            return rc;
+      sp.state = 1;
+      return 0;
+}
+
 // y = A x through the panels: panel 0 stores, later panels accumulate (stream order).
 int sell_run(const SellPlan &sp, int wpb, const double *d_x, double *d_y, int epi_mode,
              const EpiArgs &epi, cudaStream_t st) {
       const int threads = 32 * wpb;
       const int grid = blocks_for(sp.n_slices * 32, threads);
+      const bool u8 = g_knobs.sell_unroll == 8;
+      if (sp.chunk > 0) { // virtual rows: one panel, pieces of split rows go to partial sums
+            if (epi_mode == EPI_FUSED)
+                  sell_kernel<EPI_FUSED, 4, true><<<grid, threads, 0, st>>>(
+                      sp.d_soff, sp.d_perm, sp.d_ja, sp.d_as, sp.n_slices, d_x, d_y, sp.d_partial, epi);
+            else if (u8)
+                  sell_kernel<EPI_PLAIN, 8, true><<<grid, threads, 0, st>>>(
+                      sp.d_soff, sp.d_perm, sp.d_ja, sp.d_as, sp.n_slices, d_x, d_y, sp.d_partial, epi);
+            else
+                  sell_kernel<EPI_PLAIN, 4, true><<<grid, threads, 0, st>>>(
+                      sp.d_soff, sp.d_perm, sp.d_ja, sp.d_as, sp.n_slices, d_x, d_y, sp.d_partial, epi);
+            ++g_counters.launches;
+            if (sp.n_split_rows) {
+                  csr_combine_kernel<EPI_PLAIN><<<blocks_for(sp.n_split_rows, 128), 128, 0, st>>>(
+                      sp.d_split_row, sp.d_split_first, (int)sp.n_split_rows, sp.d_partial, d_y, EpiArgs{});
+                  ++g_counters.launches;
+            }
+            return 0;
+      }
       for (int p = 0; p < sp.K; ++p) {
             const long long *soff = sp.d_soff + (size_t)p * (sp.n_slices + 1);
             const int *perm = sp.d_perm + (size_t)p * sp.n_slices * 32;
-            const bool u8 = g_knobs.sell_unroll == 8;
             if (p > 0 && u8)
                   sell_kernel<EPI_ACC, 8><<<grid, threads, 0, st>>>(soff, perm, sp.d_ja, sp.d_as,
-                                                                    sp.n_slices, d_x, d_y, epi);
+                                                                    sp.n_slices, d_x, d_y, nullptr, epi);
             else if (p > 0)
                   sell_kernel<EPI_ACC, 4><<<grid, threads, 0, st>>>(soff, perm, sp.d_ja, sp.d_as,
-                                                                    sp.n_slices, d_x, d_y, epi);
+                                                                    sp.n_slices, d_x, d_y, nullptr, epi);
             else if (epi_mode == EPI_FUSED)
                   sell_kernel<EPI_FUSED, 4><<<grid, threads, 0, st>>>(soff, perm, sp.d_ja, sp.d_as,
-                                                                      sp.n_slices, d_x, d_y, epi);
+                                                                      sp.n_slices, d_x, d_y, nullptr, epi);
             else if (u8)
                   sell_kernel<EPI_PLAIN, 8><<<grid, threads, 0, st>>>(soff, perm, sp.d_ja, sp.d_as,
-                                                                      sp.n_slices, d_x, d_y, epi);
+                                                                      sp.n_slices, d_x, d_y, nullptr, epi);
             else
                   sell_kernel<EPI_PLAIN, 4><<<grid, threads, 0, st>>>(soff, perm, sp.d_ja, sp.d_as,
-                                                                      sp.n_slices, d_x, d_y, epi);
+                                                                      sp.n_slices, d_x, d_y, nullptr, epi);
             ++g_counters.launches;
       }
       return 0;
@@ -662,6 +767,16 @@ int csr_ensure_sell(spmv_b200_csr *h) {
       // gain there and cost a pass over y and the row order each (profiles/r2_kbench_c4_sell.txt).
       const bool ragged = !h->segs.empty() && !h->segs[0].regular;
       const int K = ragged && g_knobs.sell_panels <= 0 ? 1 : sell_panels_for(h->N, h->gather_span);
+      if (ragged && K == 1 && g_knobs.sell_chunk > 0) {
+            int rc;
+            if (h->wide)
+                  rc = sell_build_vrows(CsrSrc<long long>{(const long long *)h->d_irp, h->d_ja, h->d_as},
+                                        h->h_irp, h->M, h->N, g_knobs.sell_chunk, h->sell);
+            else
+                  rc = sell_build_vrows(CsrSrc<int>{(const int *)h->d_irp, h->d_ja, h->d_as}, h->h_irp,
+                                        h->M, h->N, g_knobs.sell_chunk, h->sell);
+            return rc || h->sell.state != 1 ? -1 : 0;
+      }
       std::vector<int> long_rows;
       int rc;
       if (h->wide)
@@ -782,8 +897,9 @@ int csr_run(spmv_b200_csr *h, int kernel, int wpb, long long row0, long long row
           csr_ensure_sell(h) == 0) {
             const SellPlan &sp = h->sell;
             if (epi_mode == EPI_FUSED) {
-                  if (sp.K > 1 || sp.n_long)
-                        return fail(-ENOTSUP, "fused epilogue: not available on column panels");
+                  if (sp.K > 1 || sp.n_long || sp.n_split_rows)
+                        return fail(-ENOTSUP, "fused epilogue: not available on column panels or "
+                                              "split rows");
                   if (want_dot) {
                         if (ensure_dot(&h->d_dot_partial, &h->dot_cap, sp.n_slices))
                               return -ENOMEM;
@@ -1122,6 +1238,28 @@ extern "C" int spmv_b200_sell_plan(const int *counts, int64_t M, int K, int sigm
       return 0;
 }
 
+// Same for the virtual-row form: sizes[4] = {virtual rows, slices, split rows, pieces}; dest
+// (slices*32) and soff (slices+1) may be NULL on a first call that only asks for the sizes.
+extern "C" int spmv_b200_sell_plan_vrows(const int64_t *irp, int64_t M, int chunk, int sigma,
+                                         int64_t *sizes, int *dest_out, int64_t *soff_out) {
+      if (!irp || !sizes || M < 0 || chunk < 1 || sigma < 32 || sigma % 32)
+            return fail(-EINVAL, "sell_plan_vrows: bad arguments");
+      std::vector<long long> h_irp(irp, irp + M + 1);
+      std::vector<int> vr_row, vr_j0, vr_len, dest, split_row, split_first, perm_v;
+      std::vector<long long> soff;
+      sell_virtual_rows(h_irp, M, chunk, vr_row, vr_j0, vr_len, dest, split_row, split_first);
+      long long nnz = 0;
+      const long long V = (long long)vr_row.size();
+      sell_plan_host(vr_len, V, 1, sigma, perm_v, soff, &nnz, nullptr);
+      sizes[0] = V, sizes[1] = (V + 31) / 32, sizes[2] = (int64_t)split_row.size(), sizes[3] = split_first.back();
+      if (dest_out)
+            for (size_t i = 0; i < perm_v.size(); ++i)
+                  dest_out[i] = perm_v[i] >= 0 ? dest[perm_v[i]] : -1;
+      if (soff_out)
+            std::copy(soff.begin(), soff.end(), soff_out);
+      return 0;
+}
+
 extern "C" int spmv_b200_csr_sell_download(const spmv_b200_csr *h, int64_t *soff, int *perm, int *JA,
                                            double *AS) {
       if (!h || h->sell.state != 1)
@@ -1184,8 +1322,8 @@ extern "C" int spmv_b200_csr_launches(const spmv_b200_csr *h, int kernel) {
             return -EINVAL;
       const bool sell_id = kernel == SPMV_B200_CSR_ADAPTIVE || kernel == SPMV_B200_CSR_STREAM;
       if (sell_id && h->sell.state == 1 && csr_wants_sell(const_cast<spmv_b200_csr *>(h)))
-            return h->sell.K + (h->sell.long_warp.n > 0) + (h->sell.long_block.n > 0) +
-                   (h->sell.long_split.n_rows ? 2 : 0);
+            return h->sell.K + (h->sell.n_split_rows > 0) + (h->sell.long_warp.n > 0) +
+                   (h->sell.long_block.n > 0) + (h->sell.long_split.n_rows ? 2 : 0);
       int n = 0;
       for (auto &sg : h->segs) {
             if (sg.r1 == sg.r0)
@@ -1807,6 +1945,7 @@ extern "C" int spmv_b200_set_knob(const char *key, int value) {
                    {"sell_sigma", &g_knobs.sell_sigma},
                    {"sell_panel_mb", &g_knobs.sell_panel_mb},
                    {"sell_unroll", &g_knobs.sell_unroll},
+                   {"sell_chunk", &g_knobs.sell_chunk},
                    {"sell_max_row", &g_knobs.sell_max_row},
                    {"cache", &g_knobs.cache}};
       for (auto &t : table)

@@ -266,6 +266,48 @@ def test_sell_layout_bit_exact_and_parity(sp, O, torch, name):
             sp.set_knob(k, v)
 
 
+@pytest.mark.parametrize("name", ["ragged", "rmat"])
+def test_sell_virtual_rows_bit_exact_and_parity(sp, O, torch, name):
+    """Ragged matrices: rows cut into virtual rows of `chunk` entries (no warp walks more than
+    `chunk` steps; hub rows spread over many lanes; partial sums combined in piece order).  Layout
+    bit-exact against the oracle's restatement, y within tolerance, and run-to-run identical."""
+    A = _sell_case(sp, name)
+    IRP, JA, AS = A.IRP.copy(), A.JA.copy(), A.AS.copy()
+    x = np.random.default_rng(5).uniform(-1, 1, A.N)
+    y_ref = O.csr_spmv(A.M, IRP, JA, AS, x)
+    bound = O.csr_abs_bound(A.M, IRP, JA, AS, x)
+    xd = dev(torch, x)
+    y = torch.zeros(A.M, dtype=torch.float64, device="cuda")
+    try:
+        for chunk, sigma in ((64, 16384), (8, 256), (200, 32)):
+            sp.set_knob("sell_chunk", chunk)
+            sp.set_knob("sell_sigma", sigma)
+            h = sp.CsrDevice.from_host(A)
+            info = h.sell_info(build=True)
+            assert info["state"] == 1 and info["panels"] == 1 and info["chunk"] == chunk
+            lens = np.diff(IRP)
+            assert info["split_rows"] == int((lens > chunk).sum())
+            assert info["pieces"] == int(np.ceil(lens[lens > chunk] / chunk).sum())
+            assert info["long_rows"] == 0
+            if A.M <= 6000:
+                soff, dest, ja, as_ = h.sell_download()
+                w_soff, w_dest, w_ja, w_as, _, _ = O.sellv_layout(A.M, IRP, JA, AS, sigma, chunk)
+                assert np.array_equal(soff, w_soff) and np.array_equal(dest, w_dest)
+                assert np.array_equal(ja, w_ja) and np.array_equal(as_.view(np.uint64), w_as.view(np.uint64))
+            outs = []
+            for kernel, wpb in ((2, 4), (4, 8), (2, 4)):
+                y.fill_(float("nan"))
+                h.spmv(xd, y, kernel=kernel, warps_per_block=wpb)
+                outs.append(y.cpu().numpy().copy())
+                ok, worst = O.check_tolerance(outs[-1], y_ref, bound, TOL)
+                assert ok, (name, chunk, sigma, kernel, worst)
+            assert np.array_equal(outs[0], outs[2])       # deterministic: no atomics anywhere
+            h.close()
+    finally:
+        sp.set_knob("sell_chunk", 64)
+        sp.set_knob("sell_sigma", 16384)
+
+
 def test_sell_auto_routing(sp, O, torch):
     """Who goes through SELL-P without a knob: ragged / power-law CSR (one panel while x fits
     the L2); regular rows stay on the staged kernel; and the host half of the plan (row order and

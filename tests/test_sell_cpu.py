@@ -65,3 +65,37 @@ def test_sell_plan_rejects_bad_arguments(sp):
     for K, sigma in ((0, 32), (65, 32), (1, 31), (1, 48)):
         assert L.b200.spmv_b200_sell_plan(c.ctypes.data_as(L.c_ip), 10, K, sigma, perm.ctypes.data_as(L.c_ip),
                                           soff.ctypes.data_as(L.c_i64p)) != 0
+
+
+def test_virtual_row_plan_matches_oracle(sp, O):
+    """Ragged matrices: rows longer than `chunk` are cut into virtual rows; destinations, slice
+    offsets and the split-row bookkeeping equal the oracle's restatement (oracle.sellv_layout)."""
+    L = sp._lib
+    rng = np.random.default_rng(4)
+    for trial in range(30):
+        M = int(rng.integers(1, 600))
+        N = 200
+        lens = rng.integers(0, 25, M)
+        for _ in range(int(rng.integers(0, 4))):
+            lens[rng.integers(0, M)] = int(rng.integers(60, 1500))       # hub rows
+        IRP = np.zeros(M + 1, np.int64)
+        IRP[1:] = np.cumsum(lens)
+        JA = rng.integers(0, N, int(IRP[-1])).astype(np.int32)
+        AS = rng.uniform(-1, 1, int(IRP[-1]))
+        chunk = int(rng.choice([4, 8, 64, 200]))
+        sigma = int(rng.choice([32, 256, 16384]))
+        w_soff, w_dest, _, _, w_srow, w_sfirst = O.sellv_layout(M, IRP, JA, AS, sigma, chunk)
+        sizes = np.zeros(4, np.int64)
+        assert L.b200.spmv_b200_sell_plan_vrows(IRP.ctypes.data_as(L.c_i64p), M, chunk, sigma,
+                                                sizes.ctypes.data_as(L.c_i64p), None, None) == 0
+        V, S, n_split, n_pieces = (int(v) for v in sizes)
+        assert (S, n_split, n_pieces) == (w_soff.shape[1] - 1, len(w_srow), int(w_sfirst[-1]))
+        assert V == int(np.where(lens > chunk, np.ceil(lens / chunk), 1).sum())
+        dest = np.zeros(S * 32, np.int32)
+        soff = np.zeros(S + 1, np.int64)
+        assert L.b200.spmv_b200_sell_plan_vrows(IRP.ctypes.data_as(L.c_i64p), M, chunk, sigma,
+                                                sizes.ctypes.data_as(L.c_i64p), dest.ctypes.data_as(L.c_ip),
+                                                soff.ctypes.data_as(L.c_i64p)) == 0
+        assert np.array_equal(dest, w_dest[0]), (trial, M, chunk, sigma)
+        assert np.array_equal(soff, w_soff[0]), (trial, M, chunk, sigma)
+        assert ((soff[1:] - soff[:-1]) // 32).max(initial=0) <= chunk     # no warp walks more than `chunk` steps
