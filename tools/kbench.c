@@ -26,7 +26,7 @@
 static int g_reps = 20, g_warmup = 3, g_flush = 0, g_quick = 0, g_profile = 0, g_cfg_from = -1;
 static int g_sell = 0;
 static int g_panels[16] = {1, 2, 3, 4, 6, 8, 16}, g_n_panels = 7;
-static int g_chunks[16], g_n_chunks = 0;
+static int g_chunks[16], g_n_chunks = 0, g_auto = 0;
 static double g_peak = 6559.7; /* MEASURED_PEAKS.json hbm_gbs of this pool */
 static const char *g_only = "";
 
@@ -156,6 +156,8 @@ int main(int argc, char **argv) {
                   g_profile = 1; /* only the headline kernels: for ncu captures */
             else if (!strcmp(argv[i], "--sell"))
                   g_sell = 1; /* SELL-P sweep: panels x sigma x warps/block, CSR and HLL source */
+            else if (!strcmp(argv[i], "--auto"))
+                  g_auto = 1; /* only what the library picks on its own: CSR id 2, HLL id 2 (ncu captures) */
             else if (!strcmp(argv[i], "--chunks") && i + 1 < argc) {
                   for (char *tok = strtok(argv[++i], ","); tok && g_n_chunks < 16; tok = strtok(NULL, ","))
                         g_chunks[g_n_chunks++] = atoi(tok);
@@ -211,6 +213,24 @@ int main(int argc, char **argv) {
 
       static const int wpbs[] = {2, 4, 8, 16};
       char knob[64];
+
+      if (g_auto) {
+            spmv_b200_csr *h = spmv_b200_csr_create(A);
+            if (!h) {
+                  fprintf(stderr, "kbench: %s\n", spmv_b200_last_error());
+                  return 1;
+            }
+            run_csr(&c, h, 2, 4, "auto");
+            if (strcmp(g_only, "csr")) {
+                  spmv_b200_hll *hh = spmv_b200_hll_from_csr(h);
+                  if (hh) {
+                        run_hll(&c, hh, 2, 4, "auto");
+                        spmv_b200_hll_destroy(hh);
+                  }
+            }
+            spmv_b200_csr_destroy(h);
+            return 0;
+      }
 
       if (g_n_chunks) {
             /* ragged matrices: virtual-row chunk size x unroll x warps/block */
