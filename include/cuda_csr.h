@@ -17,11 +17,16 @@
  * position, reference src/main.c:259-263):
  *   0 csr_spmv_cuda_thread_row        one thread per row
  *   1 csr_spmv_cuda_warp_row          one warp per row, shuffle reduction
- *   2 csr_spmv_cuda_halfwarp_row      ADAPTIVE: rows binned by length into
- *                                     sub-warp / warp / block-per-row groups
+ *   2 csr_spmv_cuda_halfwarp_row      ADAPTIVE by row-length profile and gather locality:
+ *                                     TMA-staged tiles (regular rows), sorted slices with
+ *                                     virtual rows (ragged rows), column panels (x > L2,
+ *                                     scattered columns); sub-warp / warp / block-per-row
+ *                                     bins on row ranges of cut shards
  *   3 csr_spmv_cuda_block_row         one CTA per row
  *   4 csr_spmv_cuda_halfwarp_row_text STREAM: value/index streams staged in
- *                                     shared memory by cp.async.bulk (TMA)
+ *                                     shared memory by cp.async.bulk (TMA); the adaptive
+ *                                     choice where staging cannot win (ragged rows,
+ *                                     scattered columns with x > L2)
  */
 #ifndef SPMV_B200_CUDA_CSR_H
 #define SPMV_B200_CUDA_CSR_H

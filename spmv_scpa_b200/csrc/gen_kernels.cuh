@@ -4,7 +4,8 @@
 // (512^3: 3.6e9 entries, not representable as one int-indexed sparse_csr and
 // far too large for a .mtx file).  Produces exactly the arrays
 // gen_stencil27_rows() (host/gen.c) produces for the same rows -- checked by
-// tests/test_gpu_generators.py through spmv_b200_csr_download().
+// tests/test_gpu_device.py::test_device_stencil_generator_matches_host through
+// spmv_b200_csr_download().
 #pragma once
 
 #include "common.cuh"

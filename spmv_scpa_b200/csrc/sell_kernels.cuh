@@ -110,7 +110,6 @@ __global__ void __launch_bounds__(1024, MIN_CTAS)
       const int lane = threadIdx.x & 31;
       const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
       const uint64_t pol_s = policy_evict_first();
-      const uint64_t pol_x = policy_evict_last();
       for (long long s = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); s < n_slices;
            s += warps) {
             const long long base = soff[s];
@@ -131,9 +130,14 @@ __global__ void __launch_bounds__(1024, MIN_CTAS)
                         a[u] = ok ? ld_stream_f64(sas + k, pol_s) : 0.0;
                         c[u] = ok ? ld_stream_s32(sja + k, pol_s) : 0;
                   }
+                  // ONE generic load per gather, its address chosen between the shared-memory
+                  // table and x: a branch here would split every gather of the batch into its own
+                  // divergent region and serialise their latencies (measured: 2x slower)
 #pragma unroll
-                  for (int u = 0; u < U; ++u)
-                        xv[u] = !okm[u] ? 0.0 : (c[u] < 0 ? s_hot[~c[u]] : ld_x(x + c[u], pol_x));
+                  for (int u = 0; u < U; ++u) {
+                        const double *p = c[u] < 0 ? s_hot + ~c[u] : x + c[u];
+                        xv[u] = okm[u] ? *p : 0.0;
+                  }
 #pragma unroll
                   for (int u = 0; u < U; u += 2) {
                         acc0 = fma(a[u], xv[u], acc0);

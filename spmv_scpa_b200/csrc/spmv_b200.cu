@@ -857,7 +857,8 @@ int csr_ensure_sell(spmv_b200_csr *h) {
       // gain there and cost a pass over y and the row order each (profiles/r2_kbench_c4_sell.txt).
       const bool ragged = !h->segs.empty() && !h->segs[0].regular;
       const int K = ragged && g_knobs.sell_panels <= 0 ? 1 : sell_panels_for(h->N, h->gather_span);
-      if (ragged && K == 1 && g_knobs.sell_chunk > 0) {
+      // virtual rows: ragged matrices, or any one-panel plan when SELL-P is forced by the knob
+      if ((ragged || g_knobs.sell == 1) && K == 1 && g_knobs.sell_panels <= 0 && g_knobs.sell_chunk > 0) {
             int rc;
             if (h->wide)
                   rc = sell_build_vrows(CsrSrc<long long>{(const long long *)h->d_irp, h->d_ja, h->d_as},

@@ -279,6 +279,7 @@ def test_sell_virtual_rows_bit_exact_and_parity(sp, O, torch, name):
     xd = dev(torch, x)
     y = torch.zeros(A.M, dtype=torch.float64, device="cuda")
     try:
+        sp.set_knob("sell", 1)        # "ragged" has 78 % of its rows in one length bin: force the route
         for chunk, sigma in ((64, 16384), (8, 256), (200, 32)):
             sp.set_knob("sell_chunk", chunk)
             sp.set_knob("sell_sigma", sigma)
@@ -304,6 +305,7 @@ def test_sell_virtual_rows_bit_exact_and_parity(sp, O, torch, name):
             assert np.array_equal(outs[0], outs[2])       # deterministic: no atomics anywhere
             h.close()
     finally:
+        sp.set_knob("sell", -1)
         sp.set_knob("sell_chunk", 64)
         sp.set_knob("sell_sigma", 16384)
 
@@ -339,10 +341,13 @@ def test_sell_hot_column_table(sp, O, torch):
             h.close()
         U = sp.gen_ragged(5000, 300)             # banded, no hub columns
         sp.set_knob("sell_hot", 64)
+        sp.set_knob("sell", 1)
         h = sp.CsrDevice.from_host(U)
-        assert h.sell_info(build=True)["hot_columns"] == 0
+        info = h.sell_info(build=True)
+        assert info["chunk"] > 0 and info["hot_columns"] == 0
         h.close()
     finally:
+        sp.set_knob("sell", -1)
         sp.set_knob("sell_hot", 0)
         sp.set_knob("sell_unroll", 4)
 
@@ -384,7 +389,7 @@ def test_fused_axpby_dot(sp, O, torch, name):
     lim = abs(alpha) * bound + abs(beta * z) * 4 * np.finfo(float).eps / 1e-12
     try:
         if name == "rmat_sell":
-            sp.set_knob("sell_max_row", 1 << 20)     # no long-row side kernels: fused is allowed
+            sp.set_knob("sell_chunk", 1 << 20)       # no row is split into pieces: fused is allowed
         h = sp.CsrDevice.from_host(A)
         handles = [("csr", h, (2, 4))]
         if name != "rmat_sell":
@@ -411,7 +416,7 @@ def test_fused_axpby_dot(sp, O, torch, name):
         for _, hd, _ in handles:
             hd.close()
     finally:
-        sp.set_knob("sell_max_row", 4096)
+        sp.set_knob("sell_chunk", 64)
 
 
 def test_handle_host_spmv(sp, O, torch):

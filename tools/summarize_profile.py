@@ -13,7 +13,11 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1] if len(sys.argv) > 1 else "c2"
 rnd = sys.argv[2] if len(sys.argv) > 2 else "r1"
-rep = os.path.join(ROOT, "gpurun_out", f"prof_{tag}.ncu-rep")
+# usage: summarize_profile.py <tag> <round> [raw.csv | report.ncu-rep] [launches.csv] [command text]
+src = sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, "gpurun_out", f"prof_{tag}.ncu-rep")
+launches_csv = sys.argv[4] if len(sys.argv) > 4 else os.path.join(ROOT, "gpurun_out", f"launches_bench_{tag}.csv")
+cmd_text = sys.argv[5] if len(sys.argv) > 5 else f"bin/kbench {tag} --profile --reps 3 --warmup 1"
+launch_cmd = sys.argv[6] if len(sys.argv) > 6 else f"python bench.py --workload {tag} --steps 20 --warmup 5 --no-cpu"
 out_dir = os.path.join(ROOT, "profiles")
 
 KEEP = ["Kernel Name", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
@@ -26,7 +30,10 @@ KEEP = ["Kernel Name", "launch__grid_size", "launch__block_size", "launch__regis
         "l1tex__data_pipe_lsu_wavefronts.sum", "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct",
         "smsp__warp_issue_stalled_barrier_per_warp_active.pct", "sm__cycles_elapsed.max"]
 
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+if src.endswith(".csv"):      # `ncu -i report --page raw --csv` already run on the GPU box (reports > 6 MB stay there)
+    raw = open(src).read()
+else:
+    raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units = rows[0], rows[1]
 idx = [hdr.index(k) for k in KEEP if k in hdr]
@@ -56,8 +63,8 @@ def to_bytes(v, unit):
 traffic = {}
 lines = [f"# ncu --set full summary, {tag}, round {rnd}",
          "",
-         "Command: `ncu --set full --clock-control none --import-source on -k regex:... bin/kbench "
-         f"{tag} --profile --reps 3 --warmup 1` (after the same command exited 0 without ncu).",
+         f"Command: `ncu --set full --clock-control none --import-source on -k regex:... {cmd_text}` "
+         "(after the same command exited 0 without ncu).",
          "Times under ncu are cold-cache and serialised (compare shares / traffic, not absolutes).",
          "",
          "| kernel | launches | time us | dram read MB | dram write MB | traffic MB | dram % of ncu peak | L2 hit % | L1 hit % | warps active % | regs | grid x block |",
@@ -73,7 +80,7 @@ for name, rs in agg.items():
                  f"{int(mean(rs, 'launch__registers_per_thread'))} | {int(mean(rs, 'launch__grid_size'))} x {int(mean(rs, 'launch__block_size'))} |")
 
 # launch list of bench.py
-lpath = os.path.join(ROOT, "gpurun_out", f"launches_bench_{tag}.csv")
+lpath = launches_csv
 if os.path.exists(lpath):
     lrows = [r for r in csv.reader(open(lpath)) if len(r) > 5]
     lh = lrows[0]
@@ -84,7 +91,7 @@ if os.path.exists(lpath):
         tot[n] = tot.get(n, 0.0) + float(r[vi].replace(",", ""))
         cnt[n] += 1
     s = sum(tot.values())
-    lines += ["", f"## launch list of `python bench.py --workload {tag} --steps 20 --warmup 5 --no-cpu` "
+    lines += ["", f"## launch list of `{launch_cmd}` "
               "(`ncu --metrics gpu__time_duration.sum --clock-control none`)", "",
               "| kernel | launches | total us | mean us | share |", "|---|---|---|---|---|"]
     for n, v in tot.items():
