@@ -88,7 +88,8 @@ int spmv_b200_host_free(void *ptr);
  * before freeing it; the host-pointer calls use registered buffers in place. */
 int spmv_b200_host_register(void *ptr, size_t bytes);
 int spmv_b200_host_unregister(void *ptr);
-/* Overwrite a scratch buffer larger than L2 so the next launch starts cold. */
+/* Overwrite a scratch buffer four times the size of the L2, then read half of it back, so the
+ * next launch starts cold AND the L2 holds no dirty lines whose write-back it would pay for. */
 int spmv_b200_flush_l2(void *stream);
 
 /* ---- resident CSR --------------------------------------------------------- */
