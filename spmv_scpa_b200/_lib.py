@@ -129,6 +129,7 @@ _sig(b200, "spmv_b200_set_timing", None, C.c_int, C.c_int)
 _sig(b200, "spmv_b200_counters", None, c_i64p, c_i64p, c_i64p)
 _sig(b200, "spmv_b200_set_knob", C.c_int, C.c_char_p, C.c_int)
 _sig(b200, "spmv_b200_host_register", C.c_int, vp, C.c_size_t)
+_sig(b200, "spmv_b200_host_copy", C.c_int, vp, vp, C.c_size_t)
 _sig(b200, "spmv_b200_host_unregister", C.c_int, vp)
 _sig(b200, "spmv_b200_set_cache_policy", C.c_int, C.c_int)
 _sig(b200, "spmv_b200_invalidate", None, vp)

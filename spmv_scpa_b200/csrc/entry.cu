@@ -14,7 +14,11 @@
 #include <omp.h>
 #include <unistd.h>
 
+#include <atomic>
+#include <condition_variable>
 #include <functional>
+#include <memory>
+#include <thread>
 
 using namespace b200;
 
@@ -109,21 +113,117 @@ int copy_threads() {
       return n;
 }
 
-// memcpy spread over an OpenMP team (pageable <-> bounce buffer)
-void parallel_copy(void *dst, const void *src, size_t bytes) {
-      constexpr size_t kBlock = 256u << 10; // small enough that an 8 MiB piece feeds every core
-      const long long blocks = (long long)((bytes + kBlock - 1) / kBlock);
-      const int nt = copy_threads();
-      if (blocks <= 2 || nt == 1) {
-            memcpy(dst, src, bytes);
-            return;
+// Worker threads for the bounce-buffer copies (pageable <-> page-locked).  Between passes they
+// sleep on a condition variable; inside a pass (CopyPool::Session) they spin on the job counter,
+// so handing them an 8 MiB piece costs microseconds -- an OpenMP parallel region per piece costs
+// a futex wake-up of the whole team under OMP_WAIT_POLICY=passive, ~100 us x 256 pieces on C5.
+class CopyPool {
+    public:
+      static CopyPool &get() {
+            static CopyPool p;
+            return p;
       }
-#pragma omp parallel for schedule(static) num_threads(nt)
-      for (long long b = 0; b < blocks; ++b) {
-            const size_t off = (size_t)b * kBlock;
-            memcpy((char *)dst + off, (const char *)src + off, std::min(kBlock, bytes - off));
+      struct Session {
+            Session() { CopyPool::get().set_active(true); }
+            ~Session() { CopyPool::get().set_active(false); }
+      };
+      // blocking: returns when all of [src, src+bytes) is at dst.  One caller at a time.
+      void copy(void *dst, const void *src, size_t bytes) {
+            const long long blocks = (long long)((bytes + kBlock - 1) / kBlock);
+            if (blocks <= 2 || workers_.empty()) {
+                  memcpy(dst, src, bytes);
+                  return;
+            }
+            std::lock_guard<std::mutex> one(caller_mu_);
+            dst_ = (char *)dst, src_ = (const char *)src, bytes_ = bytes;
+            done_.store(0);
+            next_.store(0);
+            blocks_.store(blocks); // publishes the job: everything above is visible to whoever reads it
+            job_.fetch_add(1);
+            claim_blocks(blocks);
+            while (done_.load() < blocks)
+                  ; // the last blocks are in flight on the workers
+            // Close the job, then wait for every worker that got in: a worker either announced
+            // itself (inside_ > 0) before this point and is waited for, or will find blocks_ == 0
+            // (both sides use sequentially consistent atomics), so nobody can claim a block of a
+            // later job with this job's bounds.
+            blocks_.store(0);
+            while (inside_.load() != 0)
+                  ;
       }
-}
+
+    private:
+      CopyPool() {
+            const int n = copy_threads() - 1;
+            for (int i = 0; i < n; ++i)
+                  workers_.emplace_back([this] { loop(); });
+      }
+      ~CopyPool() {
+            {
+                  std::lock_guard<std::mutex> lk(mu_);
+                  quit_ = true;
+            }
+            cv_.notify_all();
+            for (auto &t : workers_)
+                  t.join();
+      }
+      void set_active(bool on) {
+            {
+                  std::lock_guard<std::mutex> lk(mu_);
+                  active_ = on;
+            }
+            if (on)
+                  cv_.notify_all();
+      }
+      void claim_blocks(long long blocks) {
+            for (;;) {
+                  const long long b = next_.fetch_add(1);
+                  if (b >= blocks)
+                        return;
+                  const size_t off = (size_t)b * kBlock;
+                  memcpy(dst_ + off, src_ + off, std::min(kBlock, bytes_ - off));
+                  done_.fetch_add(1);
+            }
+      }
+      void work() {
+            inside_.fetch_add(1);
+            const long long blocks = blocks_.load();
+            if (blocks > 0)
+                  claim_blocks(blocks);
+            inside_.fetch_sub(1);
+      }
+      void loop() {
+            unsigned long long seen = 0;
+            for (;;) {
+                  {
+                        std::unique_lock<std::mutex> lk(mu_);
+                        cv_.wait(lk, [this] { return active_ || quit_; });
+                        if (quit_)
+                              return;
+                  }
+                  while (active_) { // spin while a pass is running
+                        const unsigned long long j = job_.load(std::memory_order_acquire);
+                        if (j != seen) {
+                              seen = j;
+                              work();
+                        }
+                  }
+            }
+      }
+      static constexpr size_t kBlock = 256u << 10;
+      std::vector<std::thread> workers_;
+      std::mutex mu_, caller_mu_;
+      std::condition_variable cv_;
+      std::atomic<bool> active_{false};
+      bool quit_ = false;
+      std::atomic<unsigned long long> job_{0};
+      std::atomic<long long> blocks_{0}, next_{0}, done_{0}, inside_{0};
+      char *dst_ = nullptr;
+      const char *src_ = nullptr;
+      size_t bytes_ = 0;
+};
+
+void parallel_copy(void *dst, const void *src, size_t bytes) { CopyPool::get().copy(dst, src, bytes); }
 
 // ------------------------------------------------------------- host-buffer pass
 // One y = A x with host x and host y.  The work is described as `n` units; unit c needs
@@ -150,6 +250,9 @@ double host_pass(long long N, long long M, const double *x, double *y, int n,
           (bounce_y && grow_pinned(&s->sy, &s->cap_sy, (size_t)M)))
             return -1.0;
 
+      std::unique_ptr<CopyPool::Session> copy_session;
+      if (bounce_x || bounce_y)
+            copy_session.reset(new CopyPool::Session());
       // kernels and downloads are queued first (they wait on events), so the host thread is
       // free to feed the bounce buffer while they run
       constexpr long long kPiece = 1ll << 20; // doubles per upload / download piece (8 MiB)
@@ -622,6 +725,16 @@ extern "C" int spmv_b200_hll_spmv_host(spmv_b200_hll *h, int kernel, int wpb, co
       if (kernel_ms)
             *kernel_ms = ms;
       return ms > 0.0 ? 0 : -EIO;
+}
+
+// The multi-threaded copy the host-buffer pass uses between pageable memory and its bounce
+// buffers, as a utility (and so that it can be exercised without a GPU).
+extern "C" int spmv_b200_host_copy(void *dst, const void *src, size_t bytes) {
+      if ((!dst || !src) && bytes)
+            return fail(-EINVAL, "host_copy: null pointer");
+      CopyPool::Session session;
+      parallel_copy(dst, src, bytes);
+      return 0;
 }
 
 extern "C" int spmv_b200_host_register(void *ptr, size_t bytes) {

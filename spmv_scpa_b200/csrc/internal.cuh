@@ -44,8 +44,8 @@ struct Knobs {
       int sell_panel_mb = 64;  // target size of a panel's x slice (C3 sweep: 64 MB beats 43 / 32 MB)
       int sell_unroll = 4;     // slot columns a lane keeps in flight (4 or 8)
       int sell_max_row = 4096; // longer rows go to the CSR long-row kernels (panel mode)
-      int sell_chunk = 64;     // ragged matrices: rows are cut into virtual rows of this many entries; 0 = off
-      int sell_hot = 0;        // ragged matrices: columns kept in shared memory (0 = off)
+      int sell_chunk = 256;    // ragged matrices: rows are cut into virtual rows of this many entries
+                               // (C4 sweep: 32/64/128/256/512/1024 -> 34/42/45/46/44/39 %); 0 = off
       int cache = 1;           // entry-point matrix cache: 0 off, 1 full content hash, 2 trust pointers
       int warmup = 1, reps = 3;
 };
@@ -136,10 +136,6 @@ struct SellPlan {
       long long n_rows = 0, n_split_rows = 0, n_partials = 0;
       int *d_split_row = nullptr, *d_split_first = nullptr;
       double *d_partial = nullptr;
-      // hot-column table (virtual-row form only): columns served from shared memory
-      int n_hot = 0;
-      int *d_hot_cols = nullptr;
-      double hot_coverage = 0.0;
       // rows too long for a slice (CSR source only): warp-per-row, CTA-per-row and split lists
       RowList long_warp;
       RowList long_block;

@@ -90,85 +90,6 @@ __global__ void __launch_bounds__(1024)
       epi_finish_warp<EPI>(epi, dot_acc, s);
 }
 
-// Hot-column variant (ragged matrices, one panel).  Power-law matrices are as skewed in their
-// columns as in their rows: on R-MAT scale 24 the 12 288 most referenced columns (0.07 % of x)
-// take 27 % of all gathers, the top 24 576 take 34 %.  Every gather that goes to the L2 moves a
-// 32-byte sector for 8 useful bytes, and the L2's sector throughput is what bounds the kernel,
-// so those columns are served from shared memory instead: at build time the H hottest columns
-// get the codes ~0 .. ~(H-1) in the slices' index array (negative = "slot of the hot table"),
-// and each persistent CTA first copies x[hot_cols[0..H)] into shared memory.
-template <int U, int MIN_CTAS>
-__global__ void __launch_bounds__(1024, MIN_CTAS)
-    sell_hot_kernel(const long long *__restrict__ soff, const int *__restrict__ perm,
-                    const int *__restrict__ ja, const double *__restrict__ as, long long n_slices,
-                    const double *__restrict__ x, double *__restrict__ y,
-                    double *__restrict__ partial, const int *__restrict__ hot_cols, int n_hot) {
-      extern __shared__ double s_hot[];
-      for (int i = threadIdx.x; i < n_hot; i += blockDim.x)
-            s_hot[i] = x[hot_cols[i]];
-      __syncthreads();
-      const int lane = threadIdx.x & 31;
-      const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
-      const uint64_t pol_s = policy_evict_first();
-      for (long long s = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); s < n_slices;
-           s += warps) {
-            const long long base = soff[s];
-            const int width = (int)((soff[s + 1] - base) >> 5);
-            const int row = perm[s * 32 + lane];
-            const double *sas = as + base;
-            const int *sja = ja + base;
-            double acc0 = 0.0, acc1 = 0.0;
-            for (int j = 0; j < width; j += U) {
-                  double a[U], xv[U];
-                  int c[U];
-                  bool okm[U];
-#pragma unroll
-                  for (int u = 0; u < U; ++u) {
-                        const int k = (j + u) * 32 + lane;
-                        const bool ok = j + u < width;
-                        okm[u] = ok;
-                        a[u] = ok ? ld_stream_f64(sas + k, pol_s) : 0.0;
-                        c[u] = ok ? ld_stream_s32(sja + k, pol_s) : 0;
-                  }
-                  // ONE generic load per gather, its address chosen between the shared-memory
-                  // table and x: a branch here would split every gather of the batch into its own
-                  // divergent region and serialise their latencies (measured: 2x slower)
-#pragma unroll
-                  for (int u = 0; u < U; ++u) {
-                        const double *p = c[u] < 0 ? s_hot + ~c[u] : x + c[u];
-                        xv[u] = okm[u] ? *p : 0.0;
-                  }
-#pragma unroll
-                  for (int u = 0; u < U; u += 2) {
-                        acc0 = fma(a[u], xv[u], acc0);
-                        acc1 = fma(a[u + 1], xv[u + 1], acc1);
-                  }
-            }
-            if (row >= 0)
-                  y[row] = acc0 + acc1;
-            else if (row < -1)
-                  partial[-2 - row] = acc0 + acc1;
-      }
-}
-
-// counts[c] += 1 for every stored entry with column c (hot-column selection)
-static __global__ void col_hist_kernel(const int *__restrict__ ja, long long n, int *__restrict__ counts) {
-      for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n;
-           k += (long long)gridDim.x * blockDim.x)
-            atomicAdd(&counts[ja[k]], 1);
-}
-
-// ja[k] = ~hot_idx[ja[k]] where the column is hot
-static __global__ void sell_mark_hot_kernel(int *__restrict__ ja, long long n,
-                                            const int *__restrict__ hot_idx) {
-      for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n;
-           k += (long long)gridDim.x * blockDim.x) {
-            const int h = hot_idx[ja[k]];
-            if (h >= 0)
-                  ja[k] = ~h;
-      }
-}
-
 // ------------------------------------------------------------------ build --
 // Row sources: the resident CSR or the resident device HLL.
 template <typename OffT>

@@ -93,7 +93,6 @@ void free_sell(SellPlan &sp) {
       free_list(sp.long_block);
       free_split(sp.long_split);
       cudaFree(sp.d_split_row), cudaFree(sp.d_split_first), cudaFree(sp.d_partial);
-      cudaFree(sp.d_hot_cols);
       sp = SellPlan();
 }
 void free_segment(Segment &sg) {
@@ -649,58 +648,6 @@ void sell_virtual_rows(const std::vector<long long> &irp, long long M, int chunk
       split_first.push_back((int)p);
 }
 
-// Hot-column table of a built virtual-row plan: the H most referenced columns (by a device
-// histogram over the CSR's index array) get negative codes in the slices' index array.  Skipped
-// when they would serve less than a tenth of the gathers (uniform columns).
-int sell_pick_hot_columns(const int *d_csr_ja, long long nnz, long long N, SellPlan &sp) {
-      const int H = (int)std::min<long long>(std::min(g_knobs.sell_hot, 28000), N);
-      if (H < 32 || nnz <= 0)
-            return 0;
-      int *d_cnt = nullptr;
-      B200_CUDA(cudaMalloc(&d_cnt, (size_t)N * sizeof(int)));
-      B200_CUDA(cudaMemset(d_cnt, 0, (size_t)N * sizeof(int)));
-      col_hist_kernel<<<1184, 256>>>(d_csr_ja, nnz, d_cnt);
-      std::vector<int> cnt((size_t)N);
-      cudaError_t e = cudaMemcpy(cnt.data(), d_cnt, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost);
-      cudaFree(d_cnt);
-      if (e != cudaSuccess)
-            return fail(-EIO, "column histogram failed: %s", cudaGetErrorString(e));
-      std::vector<int> order((size_t)N);
-      std::iota(order.begin(), order.end(), 0);
-      std::nth_element(order.begin(), order.begin() + H, order.end(), [&](int a, int b) {
-            return cnt[a] != cnt[b] ? cnt[a] > cnt[b] : a < b;
-      });
-      order.resize((size_t)H);
-      std::sort(order.begin(), order.end());
-      long long covered = 0;
-      for (int c : order)
-            covered += cnt[c];
-      sp.hot_coverage = (double)covered / (double)nnz;
-      if (sp.hot_coverage < 0.10)
-            return 0;
-      std::vector<int> hot_idx((size_t)N, -1);
-      for (int i = 0; i < H; ++i)
-            hot_idx[order[i]] = i;
-      int *d_idx = nullptr;
-      int rc = upload(&d_idx, hot_idx);
-      rc = rc ? rc : upload(&sp.d_hot_cols, order);
-      if (!rc) {
-            sell_mark_hot_kernel<<<1184, 256>>>(sp.d_ja, sp.slots, d_idx);
-            e = cudaDeviceSynchronize();
-            if (e != cudaSuccess)
-                  rc = fail(-EIO, "hot-column marking failed: %s", cudaGetErrorString(e));
-      }
-      cudaFree(d_idx);
-      if (rc) {
-            cudaFree(sp.d_hot_cols);
-            sp.d_hot_cols = nullptr;
-            return rc;
-      }
-      sp.n_hot = H;
-      g_counters.launches += 2;
-      return 0;
-}
-
 template <typename Src>
 int sell_build_vrows(const Src &src, const std::vector<long long> &irp, long long M, long long N,
                      int chunk, SellPlan &sp) {
@@ -749,52 +696,15 @@ int sell_build_vrows(const Src &src, const std::vector<long long> &irp, long lon
       if (rc)
             return rc;
       sp.state = 1;
-      if (g_knobs.sell_hot > 0 && sell_pick_hot_columns(src.ja, irp[M], N, sp))
-            cudaGetLastError(); // the table is an optimisation: without it the plain kernel runs
       return 0;
 }
 
 // y = A x through the panels: panel 0 stores, later panels accumulate (stream order).
-template <int U, int MIN_CTAS>
-int launch_sell_hot(const SellPlan &sp, size_t smem, const double *d_x, double *d_y, cudaStream_t st) {
-      auto kern = sell_hot_kernel<U, MIN_CTAS>;
-      static int occ_by_dev[kMaxDevices] = {0};
-      static size_t smem_set[kMaxDevices] = {0};
-      int dev = 0;
-      cudaGetDevice(&dev);
-      int &occ = occ_by_dev[dev % kMaxDevices];
-      if (!occ || smem_set[dev % kMaxDevices] != smem) {
-            B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 1024, smem));
-            smem_set[dev % kMaxDevices] = smem;
-            if (occ < 1)
-                  return fail(-EINVAL, "hot-column kernel does not fit on an SM (%zu bytes)", smem);
-      }
-      const int grid = (int)std::min<long long>((sp.n_slices + 31) / 32, (long long)occ * g_sm_count);
-      kern<<<grid, 1024, smem, st>>>(sp.d_soff, sp.d_perm, sp.d_ja, sp.d_as, sp.n_slices, d_x, d_y,
-                                     sp.d_partial, sp.d_hot_cols, sp.n_hot);
-      return 0;
-}
-
 int sell_run(const SellPlan &sp, int wpb, const double *d_x, double *d_y, int epi_mode,
              const EpiArgs &epi, cudaStream_t st) {
       const int threads = 32 * wpb;
       const int grid = blocks_for(sp.n_slices * 32, threads);
       const bool u8 = g_knobs.sell_unroll == 8;
-      if (sp.chunk > 0 && sp.n_hot > 0 && epi_mode != EPI_FUSED) { // hot columns from shared memory, persistent CTAs
-            const size_t smem = (size_t)sp.n_hot * sizeof(double);
-            int rc = u8 ? launch_sell_hot<8, 1>(sp, smem, d_x, d_y, st)
-                        : launch_sell_hot<4, 2>(sp, smem, d_x, d_y, st);
-            if (rc)
-                  return rc;
-            ++g_counters.launches;
-            if (sp.n_split_rows) {
-                  csr_combine_kernel<EPI_PLAIN><<<blocks_for(sp.n_split_rows, 128), 128, 0, st>>>(
-                      sp.d_split_row, sp.d_split_first, (int)sp.n_split_rows, sp.d_partial, d_y, EpiArgs{});
-                  ++g_counters.launches;
-            }
-            return 0;
-      }
       if (sp.chunk > 0) { // virtual rows: one panel, pieces of split rows go to partial sums
             if (epi_mode == EPI_FUSED)
                   sell_kernel<EPI_FUSED, 4, true><<<grid, threads, 0, st>>>(
@@ -1348,10 +1258,10 @@ extern "C" int spmv_b200_csr_sell_info(spmv_b200_csr *h, int build, int64_t *out
       if (build && h->sell.state == 0 && h->segs.size() == 1)
             csr_ensure_sell(h);
       const SellPlan &sp = h->sell;
-      const int64_t v[13] = {sp.state, sp.K, sp.sigma, sp.n_slices, sp.slots, sp.nnz_in_slices,
+      const int64_t v[11] = {sp.state, sp.K, sp.sigma, sp.n_slices, sp.slots, sp.nnz_in_slices,
                              sp.n_long, (int64_t)(h->gather_span * 1e6), sp.chunk, sp.n_split_rows,
-                             sp.n_partials, sp.n_hot, (int64_t)(sp.hot_coverage * 1e6)};
-      for (int i = 0; i < n_out && i < 13; ++i)
+                             sp.n_partials};
+      for (int i = 0; i < n_out && i < 11; ++i)
             out[i] = v[i];
       return 0;
 }
@@ -2099,7 +2009,6 @@ extern "C" int spmv_b200_set_knob(const char *key, int value) {
                    {"sell_panel_mb", &g_knobs.sell_panel_mb},
                    {"sell_unroll", &g_knobs.sell_unroll},
                    {"sell_chunk", &g_knobs.sell_chunk},
-                   {"sell_hot", &g_knobs.sell_hot},
                    {"sell_max_row", &g_knobs.sell_max_row},
                    {"cache", &g_knobs.cache}};
       for (auto &t : table)

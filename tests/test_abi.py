@@ -101,3 +101,29 @@ def test_product_never_touches_oracle():
     assert not bad, bad
     mk = open(os.path.join(ROOT, "Makefile")).read()
     assert "liboracle" not in mk.replace("$(MAKE) -C oracle", "")
+
+
+def test_host_copy_pool(sp):
+    """The copy-thread pool behind the bounce buffers of the host-pointer calls: every size from a
+    few bytes to several pieces, odd offsets, back-to-back jobs of shrinking and growing size."""
+    import ctypes as C
+    import time
+    import numpy as np
+    L = sp._lib.b200
+    rng = np.random.default_rng(0)
+    src = rng.integers(0, 255, 48 << 20, dtype=np.uint8)
+    dst = np.zeros_like(src)
+    sizes = [0, 1, 7, 4096, (256 << 10) - 1, (256 << 10) * 2 + 1, (256 << 10) * 3, 5 << 20, (8 << 20) + 13, 40 << 20,
+             (256 << 10) * 3 + 5, 17 << 20, 1 << 20]
+    for rep in range(3):
+        for n in sizes:
+            o_s, o_d = int(rng.integers(0, 4096)), int(rng.integers(0, 4096))
+            dst[:] = 0
+            assert L.spmv_b200_host_copy(C.c_void_p(dst.ctypes.data + o_d), C.c_void_p(src.ctypes.data + o_s), n) == 0
+            assert np.array_equal(dst[o_d:o_d + n], src[o_s:o_s + n])
+            assert not dst[:o_d].any() and not dst[o_d + n:].any()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        L.spmv_b200_host_copy(C.c_void_p(dst.ctypes.data), C.c_void_p(src.ctypes.data), src.nbytes)
+    gbs = 5 * src.nbytes / (time.perf_counter() - t0) / 1e9
+    assert gbs > 1.0

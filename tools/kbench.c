@@ -27,7 +27,6 @@ static int g_reps = 20, g_warmup = 3, g_flush = 0, g_quick = 0, g_profile = 0, g
 static int g_sell = 0;
 static int g_panels[16] = {1, 2, 3, 4, 6, 8, 16}, g_n_panels = 7;
 static int g_chunks[16], g_n_chunks = 0, g_auto = 0;
-static int g_hots[16] = {0}, g_n_hots = 1;
 static double g_peak = 6559.7; /* MEASURED_PEAKS.json hbm_gbs of this pool */
 static const char *g_only = "";
 
@@ -159,11 +158,7 @@ int main(int argc, char **argv) {
                   g_sell = 1; /* SELL-P sweep: panels x sigma x warps/block, CSR and HLL source */
             else if (!strcmp(argv[i], "--auto"))
                   g_auto = 1; /* only what the library picks on its own: CSR id 2, HLL id 2 (ncu captures) */
-            else if (!strcmp(argv[i], "--hot") && i + 1 < argc) {
-                  g_n_hots = 0;
-                  for (char *tok = strtok(argv[++i], ","); tok && g_n_hots < 16; tok = strtok(NULL, ","))
-                        g_hots[g_n_hots++] = atoi(tok);
-            } else if (!strcmp(argv[i], "--chunks") && i + 1 < argc) {
+            else if (!strcmp(argv[i], "--chunks") && i + 1 < argc) {
                   for (char *tok = strtok(argv[++i], ","); tok && g_n_chunks < 16; tok = strtok(NULL, ","))
                         g_chunks[g_n_chunks++] = atoi(tok);
             } else if (!strcmp(argv[i], "--panels") && i + 1 < argc) {
@@ -239,30 +234,27 @@ int main(int argc, char **argv) {
 
       if (g_n_chunks) {
             /* ragged matrices: virtual-row chunk size x unroll x warps/block */
-            int64_t info[13];
-            for (int ic = 0; ic < g_n_chunks * g_n_hots; ++ic) {
-                  const int hot = g_hots[ic / g_n_chunks];
-                  spmv_b200_set_knob("sell_hot", hot);
-                  spmv_b200_set_knob("sell_chunk", g_chunks[ic % g_n_chunks]);
+            int64_t info[11];
+            for (int ic = 0; ic < g_n_chunks; ++ic) {
+                  spmv_b200_set_knob("sell_chunk", g_chunks[ic]);
                   spmv_b200_csr *h = spmv_b200_csr_create(A);
-                  if (!h || spmv_b200_csr_sell_info(h, 1, info, 13) || info[0] != 1) {
-                        printf("CSR  sell chunk=%d BUILD FAILED: %s\n", g_chunks[ic % g_n_chunks], spmv_b200_last_error());
+                  if (!h || spmv_b200_csr_sell_info(h, 1, info, 11) || info[0] != 1) {
+                        printf("CSR  sell chunk=%d BUILD FAILED: %s\n", g_chunks[ic], spmv_b200_last_error());
                         spmv_b200_csr_destroy(h);
                         continue;
                   }
                   for (int u = 4; u <= 8; u += 4) {
                         spmv_b200_set_knob("sell_unroll", u);
-                        snprintf(knob, sizeof knob, "C=%d U=%d pad=%.1f%% H=%lld(%.0f%%)", g_chunks[ic % g_n_chunks], u,
+                        snprintf(knob, sizeof knob, "C=%d U=%d pad=%.1f%% split=%lld", g_chunks[ic], u,
                                  info[5] ? 100.0 * (info[4] - (double)info[5]) / info[5] : 0.0,
-                                 (long long)info[11], info[12] * 1e-4);
+                                 (long long)info[9]);
                         for (int w = 1; w < 4; ++w)
                               run_csr(&c, h, 2, wpbs[w], knob);
                   }
                   spmv_b200_csr_destroy(h);
             }
             spmv_b200_set_knob("sell_unroll", 4);
-            spmv_b200_set_knob("sell_chunk", 64);
-            spmv_b200_set_knob("sell_hot", 0);
+            spmv_b200_set_knob("sell_chunk", 256);
             return 0;
       }
 
