@@ -87,9 +87,6 @@ int spmv_b200_host_free(void *ptr);
 /* Page-lock / release memory the caller owns (cudaHostRegister).  The caller must unregister
  * before freeing it; the host-pointer calls use registered buffers in place. */
 int spmv_b200_host_register(void *ptr, size_t bytes);
-/* memcpy on the library's copy threads (what the host-buffer calls use between pageable memory
- * and their page-locked bounce buffers; SPMV_B200_COPY_THREADS overrides the team size). */
-int spmv_b200_host_copy(void *dst, const void *src, size_t bytes);
 int spmv_b200_host_unregister(void *ptr);
 /* Overwrite a scratch buffer four times the size of the L2, then read half of it back, so the
  * next launch starts cold AND the L2 holds no dirty lines whose write-back it would pay for. */
@@ -166,9 +163,10 @@ int spmv_b200_csr_spmv_fused(spmv_b200_csr *h, int kernel, int warps_per_block,
 int spmv_b200_csr_spmv_host(spmv_b200_csr *h, int kernel, int warps_per_block, const double *x,
                             double *y, double *kernel_ms);
 /* SELL-P plan of this matrix (column-panelled, window-sorted slices; csrc/sell_kernels.cuh):
- * out[0..11) = {state (1 built), panels, sigma, slices, padded slots, entries in slices, rows
+ * out[0..13) = {state (1 built), panels, sigma, slices, padded slots, entries in slices, rows
  * handled by the long-row kernels, gather span * 1e6, virtual-row chunk (0: none), rows split into
- * pieces, pieces}.  build != 0 builds the plan first. */
+ * pieces, pieces, columns in the shared-memory hot table, share of the gathers they serve * 1e6}.
+ * build != 0 builds the plan first. */
 int spmv_b200_csr_sell_info(spmv_b200_csr *h, int build, int64_t *out, int n_out);
 /* Device SELL-P arrays back to the host for bit-compare (any output may be NULL):
  * soff[panels*(slices+1)], perm[panels*slices*32], JA/AS[slots]. */
@@ -250,7 +248,7 @@ void spmv_b200_counters(int64_t *launches, int64_t *h2d_bytes,
 
 /* Experiment knobs used by bin/kbench sweeps and tests ("csr_stream_cfg", "hll_vec",
  * "hll_stream_cfg", "regular_lpr", "adaptive_direct", "force_wide", "pipeline", "pipe_chunks",
- * "sell", "sell_panels", "sell_sigma", "sell_panel_mb", "sell_max_row", "sell_unroll", "sell_chunk", "cache",
+ * "sell", "sell_panels", "sell_sigma", "sell_panel_mb", "sell_max_row", "sell_unroll", "sell_chunk", "sell_hot", "cache",
  * "l2_fetch_granularity").  0 or -EINVAL.  Knobs that change planning must be set before a
  * handle is created. */
 int spmv_b200_set_knob(const char *key, int value);

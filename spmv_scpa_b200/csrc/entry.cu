@@ -12,6 +12,7 @@
 #include "internal.cuh"
 
 #include <omp.h>
+#include <sched.h>
 #include <unistd.h>
 
 #include <atomic>
@@ -96,13 +97,28 @@ bool is_pinned(const void *p) {
       return at.type == cudaMemoryTypeHost;
 }
 
+// The CPUs this process may use, taken when the library is loaded.  Collective libraries narrow
+// the CALLING thread's affinity mask while they initialise (NCCL pins it next to the GPU; measured
+// on the bench box: one CPU left), and threads created afterwards inherit that mask: a copy team
+// started then would have all its members on one core.  The workers therefore take this mask.
+struct LoadMask {
+      cpu_set_t set;
+      int count = 0;
+      LoadMask() {
+            CPU_ZERO(&set);
+            if (sched_getaffinity(0, sizeof set, &set) == 0)
+                  count = CPU_COUNT(&set);
+      }
+};
+const LoadMask g_load_mask;
+
 // Threads for the bounce-buffer copies: an explicit team size, because launchers such as
-// torchrun export OMP_NUM_THREADS=1 to every rank (a num_threads clause overrides the variable);
-// the host's cores are shared between the ranks of one box (LOCAL_WORLD_SIZE).
+// torchrun export OMP_NUM_THREADS=1 to every rank; the host's cores are shared between the ranks
+// of one box (LOCAL_WORLD_SIZE).
 int copy_threads() {
       static int n = 0;
       if (!n) {
-            long cores = sysconf(_SC_NPROCESSORS_ONLN);
+            long cores = g_load_mask.count > 0 ? g_load_mask.count : sysconf(_SC_NPROCESSORS_ONLN);
             const char *lw = getenv("LOCAL_WORLD_SIZE");
             const long ranks = lw && atoi(lw) > 0 ? atoi(lw) : 1;
             n = (int)std::max(1l, std::min(16l, cores / ranks));
@@ -111,6 +127,12 @@ int copy_threads() {
                   n = atoi(env);
       }
       return n;
+}
+
+inline void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+      __builtin_ia32_pause();
+#endif
 }
 
 // Worker threads for the bounce-buffer copies (pageable <-> page-locked).  Between passes they
@@ -142,19 +164,20 @@ class CopyPool {
             job_.fetch_add(1);
             claim_blocks(blocks);
             while (done_.load() < blocks)
-                  ; // the last blocks are in flight on the workers
+                  cpu_relax(); // the last blocks are in flight on the workers
             // Close the job, then wait for every worker that got in: a worker either announced
             // itself (inside_ > 0) before this point and is waited for, or will find blocks_ == 0
             // (both sides use sequentially consistent atomics), so nobody can claim a block of a
             // later job with this job's bounds.
             blocks_.store(0);
             while (inside_.load() != 0)
-                  ;
+                  cpu_relax();
       }
 
     private:
       CopyPool() {
             const int n = copy_threads() - 1;
+            spin_ok_ = g_load_mask.count <= 0 || n + 1 <= g_load_mask.count;
             for (int i = 0; i < n; ++i)
                   workers_.emplace_back([this] { loop(); });
       }
@@ -193,6 +216,8 @@ class CopyPool {
             inside_.fetch_sub(1);
       }
       void loop() {
+            if (g_load_mask.count > 0) // not the (possibly narrowed) mask of the thread that made the pool
+                  sched_setaffinity(0, sizeof g_load_mask.set, &g_load_mask.set);
             unsigned long long seen = 0;
             for (;;) {
                   {
@@ -206,6 +231,10 @@ class CopyPool {
                         if (j != seen) {
                               seen = j;
                               work();
+                        } else if (spin_ok_) {
+                              cpu_relax();
+                        } else {
+                              std::this_thread::yield(); // more threads than CPUs: do not starve the others
                         }
                   }
             }
@@ -215,7 +244,7 @@ class CopyPool {
       std::mutex mu_, caller_mu_;
       std::condition_variable cv_;
       std::atomic<bool> active_{false};
-      bool quit_ = false;
+      bool quit_ = false, spin_ok_ = true;
       std::atomic<unsigned long long> job_{0};
       std::atomic<long long> blocks_{0}, next_{0}, done_{0}, inside_{0};
       char *dst_ = nullptr;

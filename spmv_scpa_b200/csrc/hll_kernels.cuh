@@ -264,6 +264,86 @@ __global__ void __launch_bounds__(WARPS * 32)
 }
 
 // ------------------------------------------------------------------------
+// Narrow hacks (5-point stencils: width 5, BASELINE configs[0]).  A warp that owns ONE 2 KB hack
+// spends its life in a chain of dependent loads -- hoff -> values/indices -> x -> y, each a DRAM
+// round trip while the matrix is cold -- and only two of those steps move the stream: measured
+// 54 % on the L2-flushed 80 MB matrix whatever the lane mapping (profiles/r2_kbench_c1_flush.txt).
+// Here a CTA owns G consecutive hacks.  Their values and indices are contiguous in the device
+// format, so after one look at hoff[first], hoff[last] thread 0 fetches the CTA's whole range with
+// two bulk copies (tens of KB in flight per CTA, several CTAs per SM, no registers held), and the
+// warps then walk their hacks (w, w + warps, ...) in shared memory, lane = row.  The launcher picks
+// G so that G * 32 * (widest hack of the range) fits `cap` slots.  No plan arrays, no persistent
+// ramp: every CTA starts streaming at once.
+template <int EPI>
+__global__ void __launch_bounds__(256)
+    hll_block_kernel(const long long *__restrict__ hoff, const int *__restrict__ ja,
+                     const double *__restrict__ as, long long hack0, long long hack1, int G, int cap,
+                     long long M, const double *__restrict__ x, double *__restrict__ y, EpiArgs epi) {
+      extern __shared__ __align__(128) unsigned char smem_raw[];
+      double *s_as = reinterpret_cast<double *>(smem_raw);
+      int *s_ja = reinterpret_cast<int *>(smem_raw + (size_t)cap * 8);
+      long long *s_hoff = reinterpret_cast<long long *>(smem_raw + (size_t)cap * 12);
+      uint64_t *bar = reinterpret_cast<uint64_t *>(s_hoff + G + 1);
+
+      const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, warps = blockDim.x >> 5;
+      const long long h0 = hack0 + (long long)blockIdx.x * G;
+      const int n = (int)min((long long)G, hack1 - h0);
+      const uint64_t pol_s = policy_evict_first();
+      const uint64_t pol_x = policy_evict_last();
+      if (tid == 0) {
+            mbar_init(bar, 1);
+            mbar_fence_init();
+      }
+      for (int t = tid; t <= n; t += blockDim.x)
+            s_hoff[t] = hoff[h0 + t];
+      __syncthreads();
+      const long long s0 = s_hoff[0];
+      if (tid == 0) {
+            const long long cnt = s_hoff[n] - s0; // <= cap by the launcher's choice of G
+            mbar_expect_tx(bar, (uint32_t)(cnt * 12));
+            if (cnt > 0) {
+                  bulk_g2s(s_as, as + s0, (uint32_t)(cnt * 8), bar, pol_s);
+                  bulk_g2s(s_ja, ja + s0, (uint32_t)(cnt * 4), bar, pol_s);
+            }
+      }
+      mbar_wait(bar, 0);
+
+      for (int i = warp; i < n; i += warps) {
+            const int base = (int)(s_hoff[i] - s0);
+            const int width = (int)((s_hoff[i + 1] - s_hoff[i]) >> 5);
+            const double *tas = s_as + base;
+            const int *tja = s_ja + base;
+            constexpr int U = 4;
+            double acc0 = 0.0, acc1 = 0.0;
+            for (int j = 0; j < width; j += U) {
+                  double a[U], xv[U];
+                  int c[U];
+                  bool okm[U];
+#pragma unroll
+                  for (int u = 0; u < U; ++u) {
+                        const bool ok = j + u < width;
+                        okm[u] = ok;
+                        c[u] = ok ? tja[(j + u) * 32 + lane] : 0;
+                        a[u] = ok ? tas[(j + u) * 32 + lane] : 0.0;
+                  }
+#pragma unroll
+                  for (int u = 0; u < U; ++u)
+                        xv[u] = okm[u] ? ld_x(x + c[u], pol_x) : 0.0;
+#pragma unroll
+                  for (int u = 0; u < U; u += 2) {
+                        acc0 = fma(a[u], xv[u], acc0);
+                        acc1 = fma(a[u + 1], xv[u + 1], acc1);
+                  }
+            }
+            double dot_acc = 0.0;
+            const long long r = (h0 + i) * kHack + lane;
+            if (r < M)
+                  store_y<EPI>(y, r, acc0 + acc1, epi, dot_acc);
+            epi_finish_warp<EPI>(epi, dot_acc, h0 + i - hack0);
+      }
+}
+
+// ------------------------------------------------------------------------
 // Device-side format conversion.
 // ------------------------------------------------------------------------
 

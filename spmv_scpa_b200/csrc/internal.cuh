@@ -32,6 +32,7 @@ extern Counters g_counters;
 struct Knobs {
       int csr_stream_cfg = -1; // -1: pick from warps_per_block and the row-length profile
       int hll_vec = -1;        // vector width of the HLL headline kernel; -1 = 1
+      int hll_block = -1;      // narrow hacks staged per CTA: -1 auto, 0 off, > 0 slots per CTA (forced)
       int hll_stream_cfg = -1;
       int regular_lpr = -1;    // force lanes-per-row (log2) of the adaptive base launch
       int force_wide = 0;      // use 64-bit row offsets even when NZ < 2^31 (tests)
@@ -46,6 +47,8 @@ struct Knobs {
       int sell_max_row = 4096; // longer rows go to the CSR long-row kernels (panel mode)
       int sell_chunk = 256;    // ragged matrices: rows are cut into virtual rows of this many entries
                                // (C4 sweep: 32/64/128/256/512/1024 -> 34/42/45/46/44/39 %); 0 = off
+      int sell_hot = 0;        // ragged matrices: size of the hot-column table (0 = off)
+      int sell_hot_mode = 0;   // home of the table: 0 shared memory (persistent CTAs), 1 compact global array kept in the L1
       int cache = 1;           // entry-point matrix cache: 0 off, 1 full content hash, 2 trust pointers
       int warmup = 1, reps = 3;
 };
@@ -53,6 +56,9 @@ extern Knobs g_knobs;
 
 extern int g_sm_count;
 constexpr int kMaxDevices = 64;
+// hll_block_kernel: hacks up to this width are staged per CTA, in groups of at most this many slots
+constexpr int kHllBlockMaxWidth = 12;
+constexpr int kHllBlockCap = 4096;
 
 int ensure_device();
 
@@ -136,6 +142,11 @@ struct SellPlan {
       long long n_rows = 0, n_split_rows = 0, n_partials = 0;
       int *d_split_row = nullptr, *d_split_first = nullptr;
       double *d_partial = nullptr;
+      // hot-column table (virtual-row form only): columns served from shared memory
+      int n_hot = 0;
+      int *d_hot_cols = nullptr;
+      double *d_xhot = nullptr; // x[hot_cols[..]], refreshed before every launch (L1 mode)
+      double hot_coverage = 0.0;
       // rows too long for a slice (CSR source only): warp-per-row, CTA-per-row and split lists
       RowList long_warp;
       RowList long_block;
@@ -177,6 +188,7 @@ struct spmv_b200_hll {
       double *d_as = nullptr;
       int *d_rowlen = nullptr; // entries per row (n_hacks * 32), pads excluded
       std::vector<long long> h_hoff;
+      int max_width = 0; // widest hack
       struct Tiles {
             int *d_tile_h = nullptr;
             int n_tiles = 0;

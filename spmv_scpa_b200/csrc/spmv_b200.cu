@@ -93,6 +93,7 @@ void free_sell(SellPlan &sp) {
       free_list(sp.long_block);
       free_split(sp.long_split);
       cudaFree(sp.d_split_row), cudaFree(sp.d_split_first), cudaFree(sp.d_partial);
+      cudaFree(sp.d_hot_cols), cudaFree(sp.d_xhot);
       sp = SellPlan();
 }
 void free_segment(Segment &sg) {
@@ -648,6 +649,60 @@ void sell_virtual_rows(const std::vector<long long> &irp, long long M, int chunk
       split_first.push_back((int)p);
 }
 
+// Hot-column table of a built virtual-row plan: the H most referenced columns (by a device
+// histogram over the CSR's index array) get negative codes in the slices' index array.  Skipped
+// when they would serve less than a tenth of the gathers (uniform columns).
+int sell_pick_hot_columns(const int *d_csr_ja, long long nnz, long long N, SellPlan &sp) {
+      const int H = (int)std::min<long long>(std::min(g_knobs.sell_hot, 28000), N);
+      if (H < 32 || nnz <= 0)
+            return 0;
+      int *d_cnt = nullptr;
+      B200_CUDA(cudaMalloc(&d_cnt, (size_t)N * sizeof(int)));
+      B200_CUDA(cudaMemset(d_cnt, 0, (size_t)N * sizeof(int)));
+      col_hist_kernel<<<1184, 256>>>(d_csr_ja, nnz, d_cnt);
+      std::vector<int> cnt((size_t)N);
+      cudaError_t e = cudaMemcpy(cnt.data(), d_cnt, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost);
+      cudaFree(d_cnt);
+      if (e != cudaSuccess)
+            return fail(-EIO, "column histogram failed: %s", cudaGetErrorString(e));
+      std::vector<int> order((size_t)N);
+      std::iota(order.begin(), order.end(), 0);
+      std::nth_element(order.begin(), order.begin() + H, order.end(), [&](int a, int b) {
+            return cnt[a] != cnt[b] ? cnt[a] > cnt[b] : a < b;
+      });
+      order.resize((size_t)H);
+      std::sort(order.begin(), order.end());
+      long long covered = 0;
+      for (int c : order)
+            covered += cnt[c];
+      sp.hot_coverage = (double)covered / (double)nnz;
+      if (sp.hot_coverage < 0.10)
+            return 0;
+      std::vector<int> hot_idx((size_t)N, -1);
+      for (int i = 0; i < H; ++i)
+            hot_idx[order[i]] = i;
+      int *d_idx = nullptr;
+      int rc = upload(&d_idx, hot_idx);
+      rc = rc ? rc : upload(&sp.d_hot_cols, order);
+      if (!rc && cudaMalloc(&sp.d_xhot, (size_t)H * sizeof(double)) != cudaSuccess)
+            rc = fail(-ENOMEM, "hot-column table: out of device memory");
+      if (!rc) {
+            sell_mark_hot_kernel<<<1184, 256>>>(sp.d_ja, sp.slots, d_idx);
+            e = cudaDeviceSynchronize();
+            if (e != cudaSuccess)
+                  rc = fail(-EIO, "hot-column marking failed: %s", cudaGetErrorString(e));
+      }
+      cudaFree(d_idx);
+      if (rc) {
+            cudaFree(sp.d_hot_cols), cudaFree(sp.d_xhot);
+            sp.d_hot_cols = nullptr, sp.d_xhot = nullptr;
+            return rc;
+      }
+      sp.n_hot = H;
+      g_counters.launches += 2;
+      return 0;
+}
+
 template <typename Src>
 int sell_build_vrows(const Src &src, const std::vector<long long> &irp, long long M, long long N,
                      int chunk, SellPlan &sp) {
@@ -696,15 +751,73 @@ int sell_build_vrows(const Src &src, const std::vector<long long> &irp, long lon
       if (rc)
             return rc;
       sp.state = 1;
+      if (g_knobs.sell_hot > 0 && sell_pick_hot_columns(src.ja, irp[M], N, sp))
+            cudaGetLastError(); // the table is an optimisation: without it the plain kernel runs
       return 0;
 }
 
 // y = A x through the panels: panel 0 stores, later panels accumulate (stream order).
+template <int EPI, int U, int THREADS, int MIN_CTAS, int MODE>
+int launch_sell_hot(const SellPlan &sp, const double *d_x, double *d_y, const EpiArgs &epi, cudaStream_t st) {
+      auto kern = sell_hot_kernel<EPI, U, THREADS, MIN_CTAS, MODE>;
+      if (MODE == HOT_L1) { // one slice per warp; the table is a global array the L1 keeps
+            hot_gather_kernel<<<blocks_for(sp.n_hot, 256), 256, 0, st>>>(d_x, sp.d_hot_cols, sp.n_hot, sp.d_xhot);
+            ++g_counters.launches;
+            kern<<<blocks_for(sp.n_slices * 32, THREADS), THREADS, 0, st>>>(
+                sp.d_soff, sp.d_perm, sp.d_ja, sp.d_as, sp.n_slices, d_x, d_y, sp.d_partial, sp.d_hot_cols,
+                sp.d_xhot, sp.n_hot, epi);
+            return 0;
+      }
+      const size_t smem = (size_t)sp.n_hot * sizeof(double);
+      static int occ_by_dev[kMaxDevices] = {0};
+      static size_t smem_set[kMaxDevices] = {0};
+      int dev = 0;
+      cudaGetDevice(&dev);
+      int &occ = occ_by_dev[dev % kMaxDevices];
+      if (!occ || smem_set[dev % kMaxDevices] != smem) {
+            B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem));
+            smem_set[dev % kMaxDevices] = smem;
+            if (occ < 1)
+                  return fail(-EINVAL, "hot-column kernel does not fit on an SM (%zu bytes)", smem);
+      }
+      const int grid = (int)std::min<long long>(blocks_for(sp.n_slices * 32, THREADS), (long long)occ * g_sm_count);
+      kern<<<grid, THREADS, smem, st>>>(sp.d_soff, sp.d_perm, sp.d_ja, sp.d_as, sp.n_slices, d_x, d_y,
+                                        sp.d_partial, sp.d_hot_cols, sp.d_xhot, sp.n_hot, epi);
+      return 0;
+}
+
+template <int EPI>
+int launch_sell_hot_any(const SellPlan &sp, const double *d_x, double *d_y, const EpiArgs &epi, cudaStream_t st) {
+      const bool u8 = g_knobs.sell_unroll == 8;
+      if (g_knobs.sell_hot_mode == 1) // 48 warps x 4 or 32 warps x 8 gathers in flight per SM
+            return u8 ? launch_sell_hot<EPI, 8, 512, 2, HOT_L1>(sp, d_x, d_y, epi, st)
+                      : launch_sell_hot<EPI, 4, 512, 3, HOT_L1>(sp, d_x, d_y, epi, st);
+      // two CTAs of 768 threads per SM (42 registers) while two tables fit, else one of 1 024 with
+      // twice the loads in flight per lane
+      const bool two = 2 * ((size_t)sp.n_hot * sizeof(double) + 1024) <= 227u * 1024 && !u8;
+      return two ? launch_sell_hot<EPI, 4, 768, 2, HOT_SMEM>(sp, d_x, d_y, epi, st)
+                 : launch_sell_hot<EPI, 8, 1024, 1, HOT_SMEM>(sp, d_x, d_y, epi, st);
+}
+
 int sell_run(const SellPlan &sp, int wpb, const double *d_x, double *d_y, int epi_mode,
              const EpiArgs &epi, cudaStream_t st) {
       const int threads = 32 * wpb;
       const int grid = blocks_for(sp.n_slices * 32, threads);
       const bool u8 = g_knobs.sell_unroll == 8;
+      if (sp.chunk > 0 && sp.n_hot > 0) { // hot columns from a compact table (the index array holds their codes)
+            int rc = epi_mode == EPI_FUSED ? launch_sell_hot_any<EPI_FUSED>(sp, d_x, d_y, epi, st)
+                                           : launch_sell_hot_any<EPI_PLAIN>(sp, d_x, d_y, epi, st);
+            if (rc)
+                  return rc;
+            ++g_counters.launches;
+            if (sp.n_split_rows) {
+                  csr_combine_kernel<EPI_PLAIN><<<blocks_for(sp.n_split_rows, 128), 128, 0, st>>>(
+                      sp.d_split_row, sp.d_split_first, (int)sp.n_split_rows, sp.d_partial, d_y, EpiArgs{});
+                  ++g_counters.launches;
+            }
+            return 0;
+      }
       if (sp.chunk > 0) { // virtual rows: one panel, pieces of split rows go to partial sums
             if (epi_mode == EPI_FUSED)
                   sell_kernel<EPI_FUSED, 4, true><<<grid, threads, 0, st>>>(
@@ -1258,10 +1371,10 @@ extern "C" int spmv_b200_csr_sell_info(spmv_b200_csr *h, int build, int64_t *out
       if (build && h->sell.state == 0 && h->segs.size() == 1)
             csr_ensure_sell(h);
       const SellPlan &sp = h->sell;
-      const int64_t v[11] = {sp.state, sp.K, sp.sigma, sp.n_slices, sp.slots, sp.nnz_in_slices,
+      const int64_t v[13] = {sp.state, sp.K, sp.sigma, sp.n_slices, sp.slots, sp.nnz_in_slices,
                              sp.n_long, (int64_t)(h->gather_span * 1e6), sp.chunk, sp.n_split_rows,
-                             sp.n_partials};
-      for (int i = 0; i < n_out && i < 11; ++i)
+                             sp.n_partials, sp.n_hot, (int64_t)(sp.hot_coverage * 1e6)};
+      for (int i = 0; i < n_out && i < 13; ++i)
             out[i] = v[i];
       return 0;
 }
@@ -1497,7 +1610,7 @@ int hll_alloc(spmv_b200_hll *h, const std::vector<int> &width) {
       h->h_hoff.resize((size_t)h->n_hacks + 1);
       h->h_hoff[0] = 0;
       for (long long b = 0; b < h->n_hacks; ++b)
-            h->h_hoff[b + 1] = h->h_hoff[b] + 32ll * width[b];
+            h->h_hoff[b + 1] = h->h_hoff[b] + 32ll * width[b], h->max_width = std::max(h->max_width, (int)width[b]);
       h->slots = h->h_hoff[h->n_hacks];
       B200_CUDA(cudaMalloc(&h->d_hoff, ((size_t)h->n_hacks + 1) * sizeof(long long)));
       B200_CUDA(cudaMemcpy(h->d_hoff, h->h_hoff.data(), ((size_t)h->n_hacks + 1) * sizeof(long long),
@@ -1581,6 +1694,32 @@ int hll_run_range(spmv_b200_hll *h, int kernel, int wpb, long long hack0, long l
             // and 128/64-bit variants, whose lanes share rows and split their gathers); the wide
             // variants stay selectable with the hll_vec knob.
             const int vec = g_knobs.hll_vec;
+            // narrow hacks: a CTA stages G consecutive hacks with two bulk copies (hll_block_kernel)
+            if (vec <= 1 && g_knobs.hll_block != 0 && h->max_width > 0 &&
+                (g_knobs.hll_block > 0 || h->max_width <= kHllBlockMaxWidth)) {
+                  const int cap = g_knobs.hll_block > 0 ? std::min(g_knobs.hll_block / 32 * 32, 16384) : kHllBlockCap;
+                  const int G = cap / (32 * h->max_width);
+                  if (G >= 8) {
+                        const size_t smem = (size_t)cap * 12 + ((size_t)G + 1) * 8 + 16;
+                        static size_t smem_set[2][kMaxDevices] = {{0}};
+                        const int fu = epi_mode == EPI_FUSED;
+                        if (smem_set[fu][h->device % kMaxDevices] < smem) {
+                              B200_CUDA(fu ? cudaFuncSetAttribute(hll_block_kernel<EPI_FUSED>,
+                                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                           : cudaFuncSetAttribute(hll_block_kernel<EPI_PLAIN>,
+                                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                              smem_set[fu][h->device % kMaxDevices] = smem;
+                        }
+                        const int g = (int)((n + G - 1) / G);
+                        if (fu)
+                              hll_block_kernel<EPI_FUSED><<<g, 256, smem, st>>>(h->d_hoff, h->d_ja, h->d_as, hack0, hack1,
+                                                                               G, cap, h->M, d_x, d_y, epi);
+                        else
+                              hll_block_kernel<EPI_PLAIN><<<g, 256, smem, st>>>(h->d_hoff, h->d_ja, h->d_as, hack0, hack1,
+                                                                               G, cap, h->M, d_x, d_y, epi);
+                        break;
+                  }
+            }
             if (epi_mode == EPI_FUSED)
                   hll_warp_kernel<1, EPI_FUSED><<<grid, threads, 0, st>>>(
                       h->d_hoff, h->d_ja, h->d_as, hack0, hack1, h->M, d_x, d_y, epi);
@@ -1997,6 +2136,7 @@ extern "C" int spmv_b200_set_knob(const char *key, int value) {
             int *slot;
       } table[] = {{"csr_stream_cfg", &g_knobs.csr_stream_cfg},
                    {"hll_vec", &g_knobs.hll_vec},
+                   {"hll_block", &g_knobs.hll_block},
                    {"hll_stream_cfg", &g_knobs.hll_stream_cfg},
                    {"regular_lpr", &g_knobs.regular_lpr},
                    {"force_wide", &g_knobs.force_wide},
@@ -2009,6 +2149,8 @@ extern "C" int spmv_b200_set_knob(const char *key, int value) {
                    {"sell_panel_mb", &g_knobs.sell_panel_mb},
                    {"sell_unroll", &g_knobs.sell_unroll},
                    {"sell_chunk", &g_knobs.sell_chunk},
+                   {"sell_hot", &g_knobs.sell_hot},
+                   {"sell_hot_mode", &g_knobs.sell_hot_mode},
                    {"sell_max_row", &g_knobs.sell_max_row},
                    {"cache", &g_knobs.cache}};
       for (auto &t : table)

@@ -310,6 +310,51 @@ def test_sell_virtual_rows_bit_exact_and_parity(sp, O, torch, name):
         sp.set_knob("sell_sigma", 16384)
 
 
+def test_sell_hot_column_table(sp, O, torch):
+    """Power-law matrices: the most referenced columns are served from shared memory (codes ~i in
+    the slices' index array).  Same y within tolerance for several table sizes and both unroll
+    depths; a matrix with uniform columns gets no table (it would serve < 10 % of the gathers)."""
+    A = sp.gen_rmat(15, 16)
+    IRP, JA, AS = A.IRP.copy(), A.JA.copy(), A.AS.copy()
+    x = np.random.default_rng(9).uniform(-1, 1, A.N)
+    y_ref = O.csr_spmv(A.M, IRP, JA, AS, x)
+    bound = O.csr_abs_bound(A.M, IRP, JA, AS, x)
+    xd = dev(torch, x)
+    y = torch.zeros(A.M, dtype=torch.float64, device="cuda")
+    try:
+        for hot in (64, 1000, 12288, 24576):
+            sp.set_knob("sell_hot", hot)
+            h = sp.CsrDevice.from_host(A)
+            info = h.sell_info(build=True)
+            assert info["state"] == 1 and info["hot_columns"] == min(hot, 28000) and info["hot_coverage_ppm"] > 100000
+            _, _, ja, _ = h.sell_download()
+            cnt = np.bincount(JA, minlength=A.N)
+            top = np.sort(cnt)[::-1][:info["hot_columns"]].sum() / A.NZ
+            assert abs(info["hot_coverage_ppm"] * 1e-6 - top) < 1e-6
+            assert (ja < 0).any() and ja.min() >= -info["hot_columns"]
+            for mode in (0, 1):                   # table in shared memory / compact global array kept in the L1
+                sp.set_knob("sell_hot_mode", mode)
+                for unroll in (4, 8):
+                    sp.set_knob("sell_unroll", unroll)
+                    y.fill_(float("nan"))
+                    h.spmv(xd, y, kernel=2, warps_per_block=4)
+                    ok, worst = O.check_tolerance(y.cpu().numpy(), y_ref, bound, TOL)
+                    assert ok, (hot, mode, unroll, worst)
+            h.close()
+        U = sp.gen_ragged(5000, 300)             # banded, no hub columns
+        sp.set_knob("sell_hot", 64)
+        sp.set_knob("sell", 1)
+        h = sp.CsrDevice.from_host(U)
+        info = h.sell_info(build=True)
+        assert info["chunk"] > 0 and info["hot_columns"] == 0
+        h.close()
+    finally:
+        sp.set_knob("sell", -1)
+        sp.set_knob("sell_hot", 0)
+        sp.set_knob("sell_hot_mode", 0)
+        sp.set_knob("sell_unroll", 4)
+
+
 def test_sell_auto_routing(sp, O, torch):
     """Who goes through SELL-P without a knob: ragged / power-law CSR (one panel while x fits
     the L2); regular rows stay on the staged kernel; and the host half of the plan (row order and
@@ -375,6 +420,45 @@ def test_fused_axpby_dot(sp, O, torch, name):
             hd.close()
     finally:
         sp.set_knob("sell_chunk", 256)
+
+
+def test_hll_block_staged_kernel(sp, O, torch):
+    """HLL id 2 on narrow hacks: a CTA stages a group of consecutive hacks with two bulk copies
+    (hll_block_kernel).  Same y as the reference serial CSR for every group size, with empty hacks,
+    hacks of different widths, a last group that is cut short, hack ranges (the host-buffer
+    pipeline's launches) and wide matrices that must stay on the warp-per-hack kernel."""
+    rng = np.random.default_rng(21)
+    M, N = 32 * 211 + 13, 5000
+    lens = rng.integers(0, 11, M)
+    lens[32 * 40:32 * 44] = 0                                 # four empty hacks
+    lens[32 * 100:32 * 101] = 1
+    IRP = np.zeros(M + 1, np.int32)
+    IRP[1:] = np.cumsum(lens)
+    JA = np.concatenate([np.sort(rng.choice(N, l, replace=False)) for l in lens]).astype(np.int32)
+    AS = rng.uniform(-1, 1, JA.size)
+    cases = [("narrow", sp.csr_from_arrays("narrow", M, N, IRP, JA, AS)), ("poisson", sp.gen_poisson2d(123, 77)),
+             ("stencil27", sp.gen_stencil27(14, 13, 12))]
+    try:
+        for name, A in cases:
+            irp, ja, as_ = A.IRP.copy(), A.JA.copy(), A.AS.copy()
+            x = rng.uniform(-1, 1, A.N)
+            y_ref = O.csr_spmv(A.M, irp, ja, as_, x)
+            bound = O.csr_abs_bound(A.M, irp, ja, as_, x)
+            xd = dev(torch, x)
+            for block in (-1, 0, 512, 1024, 4096, 16384):
+                sp.set_knob("hll_block", block)
+                for h in (sp.CsrDevice.from_host(A).to_hll(), sp.HllDevice.from_host(sp.csr_to_hll(A, True))):
+                    y = torch.full((A.M,), float("nan"), dtype=torch.float64, device="cuda")
+                    h.spmv(xd, y, kernel=2, warps_per_block=4)
+                    ok, worst = O.check_tolerance(y.cpu().numpy(), y_ref, bound, TOL)
+                    assert ok, (name, block, worst)
+                    yh = np.full(A.M, np.nan)
+                    h.spmv_host(x, yh, kernel=2)              # launches on hack ranges
+                    ok, worst = O.check_tolerance(yh, y_ref, bound, TOL)
+                    assert ok, (name, block, "host", worst)
+                    h.close()
+    finally:
+        sp.set_knob("hll_block", -1)
 
 
 def test_handle_host_spmv(sp, O, torch):

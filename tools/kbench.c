@@ -27,6 +27,7 @@ static int g_reps = 20, g_warmup = 3, g_flush = 0, g_quick = 0, g_profile = 0, g
 static int g_sell = 0;
 static int g_panels[16] = {1, 2, 3, 4, 6, 8, 16}, g_n_panels = 7;
 static int g_chunks[16], g_n_chunks = 0, g_auto = 0;
+static int g_hots[16] = {0}, g_n_hots = 1;
 static double g_peak = 6559.7; /* MEASURED_PEAKS.json hbm_gbs of this pool */
 static const char *g_only = "";
 
@@ -158,7 +159,11 @@ int main(int argc, char **argv) {
                   g_sell = 1; /* SELL-P sweep: panels x sigma x warps/block, CSR and HLL source */
             else if (!strcmp(argv[i], "--auto"))
                   g_auto = 1; /* only what the library picks on its own: CSR id 2, HLL id 2 (ncu captures) */
-            else if (!strcmp(argv[i], "--chunks") && i + 1 < argc) {
+            else if (!strcmp(argv[i], "--hot") && i + 1 < argc) {
+                  g_n_hots = 0;
+                  for (char *tok = strtok(argv[++i], ","); tok && g_n_hots < 16; tok = strtok(NULL, ","))
+                        g_hots[g_n_hots++] = atoi(tok);
+            } else if (!strcmp(argv[i], "--chunks") && i + 1 < argc) {
                   for (char *tok = strtok(argv[++i], ","); tok && g_n_chunks < 16; tok = strtok(NULL, ","))
                         g_chunks[g_n_chunks++] = atoi(tok);
             } else if (!strcmp(argv[i], "--panels") && i + 1 < argc) {
@@ -234,27 +239,35 @@ int main(int argc, char **argv) {
 
       if (g_n_chunks) {
             /* ragged matrices: virtual-row chunk size x unroll x warps/block */
-            int64_t info[11];
-            for (int ic = 0; ic < g_n_chunks; ++ic) {
-                  spmv_b200_set_knob("sell_chunk", g_chunks[ic]);
+            int64_t info[13];
+            for (int ic = 0; ic < g_n_chunks * g_n_hots; ++ic) {
+                  const int hot = g_hots[ic / g_n_chunks];
+                  spmv_b200_set_knob("sell_hot", hot);
+                  spmv_b200_set_knob("sell_chunk", g_chunks[ic % g_n_chunks]);
                   spmv_b200_csr *h = spmv_b200_csr_create(A);
-                  if (!h || spmv_b200_csr_sell_info(h, 1, info, 11) || info[0] != 1) {
-                        printf("CSR  sell chunk=%d BUILD FAILED: %s\n", g_chunks[ic], spmv_b200_last_error());
+                  if (!h || spmv_b200_csr_sell_info(h, 1, info, 13) || info[0] != 1) {
+                        printf("CSR  sell chunk=%d BUILD FAILED: %s\n", g_chunks[ic % g_n_chunks], spmv_b200_last_error());
                         spmv_b200_csr_destroy(h);
                         continue;
                   }
-                  for (int u = 4; u <= 8; u += 4) {
-                        spmv_b200_set_knob("sell_unroll", u);
-                        snprintf(knob, sizeof knob, "C=%d U=%d pad=%.1f%% split=%lld", g_chunks[ic], u,
-                                 info[5] ? 100.0 * (info[4] - (double)info[5]) / info[5] : 0.0,
-                                 (long long)info[9]);
-                        for (int w = 1; w < 4; ++w)
-                              run_csr(&c, h, 2, wpbs[w], knob);
-                  }
+                  /* hot table: both homes (0 shared memory, persistent CTAs: warps/block is
+                   * ignored; 1 compact global array kept in the L1) */
+                  for (int mode = 0; mode < (info[11] ? 2 : 1); ++mode)
+                        for (int u = 4; u <= 8; u += 4) {
+                              spmv_b200_set_knob("sell_hot_mode", mode);
+                              spmv_b200_set_knob("sell_unroll", u);
+                              snprintf(knob, sizeof knob, "C=%d U=%d pad=%.1f%% H=%lld(%.0f%%)%s", g_chunks[ic % g_n_chunks], u,
+                                       info[5] ? 100.0 * (info[4] - (double)info[5]) / info[5] : 0.0,
+                                       (long long)info[11], info[12] * 1e-4, !info[11] ? "" : mode ? " L1" : " smem");
+                              for (int w = (info[11] && !mode) ? 3 : 1; w < 4; ++w)
+                                    run_csr(&c, h, 2, wpbs[w], knob);
+                        }
                   spmv_b200_csr_destroy(h);
             }
             spmv_b200_set_knob("sell_unroll", 4);
             spmv_b200_set_knob("sell_chunk", 256);
+            spmv_b200_set_knob("sell_hot", 0);
+            spmv_b200_set_knob("sell_hot_mode", 0);
             return 0;
       }
 
@@ -430,6 +443,7 @@ int main(int argc, char **argv) {
                    100.0 * (spmv_b200_hll_slots(hh) - (double)A->NZ) / (A->NZ ? A->NZ : 1));
             for (int w = 0; w < 4; ++w)
                   run_hll(&c, hh, 1, wpbs[w], "-");
+            spmv_b200_set_knob("hll_block", 0); /* warp per hack, whatever the width */
             for (int v = 1; v <= 4; v *= 2) {
                   spmv_b200_set_knob("hll_vec", v);
                   snprintf(knob, sizeof knob, "vec=%d", v);
@@ -437,6 +451,16 @@ int main(int argc, char **argv) {
                         run_hll(&c, hh, 2, wpbs[w], knob);
             }
             spmv_b200_set_knob("hll_vec", -1);
+            /* hacks staged per CTA (bulk copies): what the library picks, then forced group sizes */
+            spmv_b200_set_knob("hll_block", -1);
+            run_hll(&c, hh, 2, 4, "block=auto");
+            static const int caps[] = {1024, 2048, 4096, 8192, 16384};
+            for (int i = 0; i < 5; ++i) {
+                  spmv_b200_set_knob("hll_block", caps[i]);
+                  snprintf(knob, sizeof knob, "block=%d", caps[i]);
+                  run_hll(&c, hh, 2, 4, knob);
+            }
+            spmv_b200_set_knob("hll_block", -1);
             for (int cfg = 0; cfg < 3; ++cfg) {
                   spmv_b200_set_knob("hll_stream_cfg", cfg);
                   snprintf(knob, sizeof knob, "cfg=%d", cfg);
