@@ -539,4 +539,116 @@ __global__ void __launch_bounds__(THREADS + (WS ? 32 : 0))
       epi_finish_warp<EPI>(epi, dot_acc, (long long)blockIdx.x * CWARPS + (tid >> 5));
 }
 
+// ------------------------------------------------------------------------
+// Short regular rows (5-point stencils, BASELINE configs[0]): the CSR twin of hll_pipe_kernel.
+// Persistent warps; a warp owns groups of 32 consecutive rows (g, g + W, ...), whose entries are
+// one contiguous piece of ja / as: lane 0 fetches it (rounded out to multiples of 4 entries, the
+// arrays carry 16 spare entries) with two bulk copies into the warp's private ring of STAGES
+// buffers, every lane then walks its own row in shared memory (row starts are ~5 words apart:
+// conflict-free), and the row offsets of the group after next are loaded while the current one is
+// computed.  No CTA-wide synchronisation, no plan arrays.  The launcher guarantees rows <= 8.
+template <int STAGES, typename OffT>
+__global__ void __launch_bounds__(256)
+    csr_pipe_kernel(const OffT *__restrict__ irp, const int *__restrict__ ja,
+                    const double *__restrict__ as, long long row0, long long row1, int capw,
+                    const double *__restrict__ x, double *__restrict__ y) {
+      extern __shared__ __align__(128) unsigned char smem_raw[];
+      const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
+      unsigned char *ring = smem_raw + (size_t)warp * STAGES * capw * 12;
+      uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)wpc * STAGES * capw * 12) + warp * STAGES;
+      const long long W = (long long)gridDim.x * wpc;
+      const long long first = (long long)blockIdx.x * wpc + warp;
+      const long long n_groups = (row1 - row0 + 31) >> 5;
+      const uint64_t pol_s = policy_evict_first();
+      const uint64_t pol_x = policy_evict_last();
+      if (lane == 0) {
+#pragma unroll
+            for (int s = 0; s < STAGES; ++s)
+                  mbar_init(&bars[s], 1);
+            mbar_fence_init();
+      }
+      __syncwarp();
+
+      // row offsets of group g: this lane's row [lo, hi), the group's entries [k_lo, k_hi)
+      auto offsets = [&](long long g, long long &lo, long long &hi, long long &k_lo, long long &k_hi) {
+            const long long r = row0 + (g << 5) + lane;
+            lo = (long long)irp[min(r, row1)];
+            k_hi = (long long)irp[min(row0 + ((g + 1) << 5), row1)];
+            hi = __shfl_down_sync(0xffffffffu, lo, 1);
+            if (lane == 31)
+                  hi = k_hi;
+            k_lo = __shfl_sync(0xffffffffu, lo, 0);
+      };
+      int s0[STAGES], s1[STAGES]; // this lane's entries inside the stage's buffer
+      auto fetch = [&](int s, long long lo, long long hi, long long k_lo, long long k_hi) {
+            const long long ka = k_lo & ~3ll, kb = (k_hi + 3) & ~3ll;
+            s0[s] = (int)(lo - ka), s1[s] = (int)(hi - ka);
+            if (lane == 0) {
+                  const long long cnt = kb - ka;
+                  mbar_expect_tx(&bars[s], (uint32_t)(cnt * 12));
+                  if (cnt > 0) {
+                        bulk_g2s(ring + (size_t)s * capw * 12, as + ka, (uint32_t)(cnt * 8), &bars[s], pol_s);
+                        bulk_g2s(ring + (size_t)s * capw * 12 + (size_t)capw * 8, ja + ka, (uint32_t)(cnt * 4),
+                                 &bars[s], pol_s);
+                  }
+            }
+      };
+#pragma unroll
+      for (int s = 0; s < STAGES; ++s) {
+            const long long g = first + s * W;
+            s0[s] = s1[s] = 0;
+            if (g < n_groups) {
+                  long long lo, hi, k_lo, k_hi;
+                  offsets(g, lo, hi, k_lo, k_hi);
+                  fetch(s, lo, hi, k_lo, k_hi);
+            }
+      }
+      for (long long i = 0;; i += STAGES) {
+            const uint32_t parity = (uint32_t)(i / STAGES) & 1u;
+#pragma unroll
+            for (int s = 0; s < STAGES; ++s) {
+                  const long long g = first + (i + s) * W;
+                  if (g >= n_groups)
+                        return; // whole warp
+                  const long long gn = g + STAGES * W;
+                  long long lo = 0, hi = 0, k_lo = 0, k_hi = 0;
+                  if (gn < n_groups)
+                        offsets(gn, lo, hi, k_lo, k_hi); // on their way while this group is computed
+                  mbar_wait(&bars[s], parity);
+                  const double *tas = reinterpret_cast<const double *>(ring + (size_t)s * capw * 12);
+                  const int *tja = reinterpret_cast<const int *>(ring + (size_t)s * capw * 12 + (size_t)capw * 8);
+                  const int k0 = s0[s], len = s1[s] - k0;
+                  const int wmax = __reduce_max_sync(0xffffffffu, len);
+                  constexpr int U = 8;
+                  double acc0 = 0.0, acc1 = 0.0;
+                  for (int j = 0; j < wmax; j += U) {
+                        double a[U], xv[U];
+                        int c[U];
+                        bool okm[U];
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                              const bool ok = j + u < len;
+                              okm[u] = ok;
+                              c[u] = ok ? tja[k0 + j + u] : 0;
+                              a[u] = ok ? tas[k0 + j + u] : 0.0;
+                        }
+#pragma unroll
+                        for (int u = 0; u < U; ++u)
+                              xv[u] = okm[u] ? ld_x(x + c[u], pol_x) : 0.0;
+#pragma unroll
+                        for (int u = 0; u < U; u += 2) {
+                              acc0 = fma(a[u], xv[u], acc0);
+                              acc1 = fma(a[u + 1], xv[u + 1], acc1);
+                        }
+                  }
+                  __syncwarp(); // every lane has read the stage: it may be overwritten
+                  if (gn < n_groups)
+                        fetch(s, lo, hi, k_lo, k_hi);
+                  const long long r = row0 + (g << 5) + lane;
+                  if (r < row1)
+                        y[r] = acc0 + acc1;
+            }
+      }
+}
+
 } // namespace b200

@@ -13,6 +13,9 @@
 
 #include <omp.h>
 #include <sched.h>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 #include <unistd.h>
 
 #include <atomic>
@@ -97,20 +100,30 @@ bool is_pinned(const void *p) {
       return at.type == cudaMemoryTypeHost;
 }
 
-// The CPUs this process may use, taken when the library is loaded.  Collective libraries narrow
-// the CALLING thread's affinity mask while they initialise (NCCL pins it next to the GPU; measured
-// on the bench box: one CPU left), and threads created afterwards inherit that mask: a copy team
-// started then would have all its members on one core.  The workers therefore take this mask.
-struct LoadMask {
+// The CPUs the copy team may use.  Not the calling thread's mask: OpenMP runtimes bind the initial
+// thread to ONE place under OMP_PROC_BIND (bench.py sets it for the CPU baseline; measured on the
+// bench box: one CPU left) and collective libraries pin it next to the GPU, and threads created
+// afterwards inherit that mask -- a team started then sits on one core.  A scratch thread asks for
+// every CPU instead; the kernel answers with what the container's cpuset really allows.
+struct AllowedCpus {
       cpu_set_t set;
       int count = 0;
-      LoadMask() {
+      AllowedCpus() {
             CPU_ZERO(&set);
-            if (sched_getaffinity(0, sizeof set, &set) == 0)
-                  count = CPU_COUNT(&set);
+            std::thread([this] {
+                  cpu_set_t all;
+                  CPU_ZERO(&all);
+                  for (int i = 0; i < CPU_SETSIZE; ++i)
+                        CPU_SET(i, &all);
+                  if (sched_setaffinity(0, sizeof all, &all) == 0 && sched_getaffinity(0, sizeof set, &set) == 0)
+                        count = CPU_COUNT(&set);
+            }).join();
       }
 };
-const LoadMask g_load_mask;
+const AllowedCpus &allowed_cpus() {
+      static const AllowedCpus a;
+      return a;
+}
 
 // Threads for the bounce-buffer copies: an explicit team size, because launchers such as
 // torchrun export OMP_NUM_THREADS=1 to every rank; the host's cores are shared between the ranks
@@ -118,7 +131,7 @@ const LoadMask g_load_mask;
 int copy_threads() {
       static int n = 0;
       if (!n) {
-            long cores = g_load_mask.count > 0 ? g_load_mask.count : sysconf(_SC_NPROCESSORS_ONLN);
+            long cores = allowed_cpus().count > 0 ? allowed_cpus().count : sysconf(_SC_NPROCESSORS_ONLN);
             const char *lw = getenv("LOCAL_WORLD_SIZE");
             const long ranks = lw && atoi(lw) > 0 ? atoi(lw) : 1;
             n = (int)std::max(1l, std::min(16l, cores / ranks));
@@ -127,6 +140,48 @@ int copy_threads() {
                   n = atoi(env);
       }
       return n;
+}
+
+// Block copy with non-temporal stores: the bounce-buffer copies are far larger than the caches and
+// their destination is not read again by this core (the copy engine or the caller's next phase
+// reads it from DRAM), so the read-for-ownership a plain store pays is pure waste -- one third of
+// the copy's memory traffic.
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) void copy_block_nt(char *dst, const char *src, size_t n) {
+      size_t head = (size_t)(-(uintptr_t)dst) & 31;
+      if (head > n)
+            head = n;
+      memcpy(dst, src, head);
+      dst += head, src += head, n -= head;
+      size_t i = 0;
+      for (; i + 128 <= n; i += 128) {
+            const __m256i a = _mm256_loadu_si256((const __m256i *)(src + i));
+            const __m256i b = _mm256_loadu_si256((const __m256i *)(src + i + 32));
+            const __m256i c = _mm256_loadu_si256((const __m256i *)(src + i + 64));
+            const __m256i d = _mm256_loadu_si256((const __m256i *)(src + i + 96));
+            _mm256_stream_si256((__m256i *)(dst + i), a);
+            _mm256_stream_si256((__m256i *)(dst + i + 32), b);
+            _mm256_stream_si256((__m256i *)(dst + i + 64), c);
+            _mm256_stream_si256((__m256i *)(dst + i + 96), d);
+      }
+      for (; i + 32 <= n; i += 32)
+            _mm256_stream_si256((__m256i *)(dst + i), _mm256_loadu_si256((const __m256i *)(src + i)));
+      memcpy(dst + i, src + i, n - i);
+      _mm_sfence();
+}
+bool have_avx2() {
+      static const bool v = __builtin_cpu_supports("avx2");
+      return v;
+}
+#endif
+inline void copy_block(char *dst, const char *src, size_t n) {
+#if defined(__x86_64__)
+      if (n >= 4096 && have_avx2()) {
+            copy_block_nt(dst, src, n);
+            return;
+      }
+#endif
+      memcpy(dst, src, n);
 }
 
 inline void cpu_relax() {
@@ -153,7 +208,7 @@ class CopyPool {
       void copy(void *dst, const void *src, size_t bytes) {
             const long long blocks = (long long)((bytes + kBlock - 1) / kBlock);
             if (blocks <= 2 || workers_.empty()) {
-                  memcpy(dst, src, bytes);
+                  copy_block((char *)dst, (const char *)src, bytes);
                   return;
             }
             std::lock_guard<std::mutex> one(caller_mu_);
@@ -177,7 +232,7 @@ class CopyPool {
     private:
       CopyPool() {
             const int n = copy_threads() - 1;
-            spin_ok_ = g_load_mask.count <= 0 || n + 1 <= g_load_mask.count;
+            spin_ok_ = allowed_cpus().count <= 0 || n + 1 <= allowed_cpus().count;
             for (int i = 0; i < n; ++i)
                   workers_.emplace_back([this] { loop(); });
       }
@@ -204,7 +259,7 @@ class CopyPool {
                   if (b >= blocks)
                         return;
                   const size_t off = (size_t)b * kBlock;
-                  memcpy(dst_ + off, src_ + off, std::min(kBlock, bytes_ - off));
+                  copy_block(dst_ + off, src_ + off, std::min(kBlock, bytes_ - off));
                   done_.fetch_add(1);
             }
       }
@@ -216,8 +271,8 @@ class CopyPool {
             inside_.fetch_sub(1);
       }
       void loop() {
-            if (g_load_mask.count > 0) // not the (possibly narrowed) mask of the thread that made the pool
-                  sched_setaffinity(0, sizeof g_load_mask.set, &g_load_mask.set);
+            if (allowed_cpus().count > 0) // not the (possibly narrowed) mask of the thread that made the pool
+                  sched_setaffinity(0, sizeof allowed_cpus().set, &allowed_cpus().set);
             unsigned long long seen = 0;
             for (;;) {
                   {

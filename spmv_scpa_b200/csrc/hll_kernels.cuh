@@ -265,81 +265,106 @@ __global__ void __launch_bounds__(WARPS * 32)
 
 // ------------------------------------------------------------------------
 // Narrow hacks (5-point stencils: width 5, BASELINE configs[0]).  A warp that owns ONE 2 KB hack
-// spends its life in a chain of dependent loads -- hoff -> values/indices -> x -> y, each a DRAM
-// round trip while the matrix is cold -- and only two of those steps move the stream: measured
-// 54 % on the L2-flushed 80 MB matrix whatever the lane mapping (profiles/r2_kbench_c1_flush.txt).
-// Here a CTA owns G consecutive hacks.  Their values and indices are contiguous in the device
-// format, so after one look at hoff[first], hoff[last] thread 0 fetches the CTA's whole range with
-// two bulk copies (tens of KB in flight per CTA, several CTAs per SM, no registers held), and the
-// warps then walk their hacks (w, w + warps, ...) in shared memory, lane = row.  The launcher picks
-// G so that G * 32 * (widest hack of the range) fits `cap` slots.  No plan arrays, no persistent
-// ramp: every CTA starts streaming at once.
-template <int EPI>
+// lives through a chain of dependent loads -- hoff -> values/indices (two batches) -> x -> y, each
+// a DRAM round trip (~1.1 us) while the matrix is cold -- and the SM's 64 warps only have 2 KB
+// each to hide it with: 3.3 waves x 5.5 us = the 20 us measured on the L2-flushed 80 MB matrix
+// (59 %, whatever the lane mapping or group size; profiles/r2_kbench_c1_*.txt, r2_c1_ncu_summary.md).
+// Here every warp is persistent and runs its OWN software pipeline: lane 0 fetches the values and
+// indices of the warp's next hacks with bulk copies into a private ring of STAGES shared-memory
+// buffers (one mbarrier per stage, no CTA-wide synchronisation anywhere), the offsets of the hack
+// after those are already in registers, and the only latency left on the critical path of a hack
+// is its gather of x.  Hacks are dealt round-robin (warp w: w, w + W, ...), so neighbouring warps
+// stream neighbouring memory.
+template <int STAGES, int EPI>
 __global__ void __launch_bounds__(256)
-    hll_block_kernel(const long long *__restrict__ hoff, const int *__restrict__ ja,
-                     const double *__restrict__ as, long long hack0, long long hack1, int G, int cap,
-                     long long M, const double *__restrict__ x, double *__restrict__ y, EpiArgs epi) {
+    hll_pipe_kernel(const long long *__restrict__ hoff, const int *__restrict__ ja,
+                    const double *__restrict__ as, long long hack0, long long hack1, int capw,
+                    long long M, const double *__restrict__ x, double *__restrict__ y, EpiArgs epi) {
       extern __shared__ __align__(128) unsigned char smem_raw[];
-      double *s_as = reinterpret_cast<double *>(smem_raw);
-      int *s_ja = reinterpret_cast<int *>(smem_raw + (size_t)cap * 8);
-      long long *s_hoff = reinterpret_cast<long long *>(smem_raw + (size_t)cap * 12);
-      uint64_t *bar = reinterpret_cast<uint64_t *>(s_hoff + G + 1);
-
-      const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, warps = blockDim.x >> 5;
-      const long long h0 = hack0 + (long long)blockIdx.x * G;
-      const int n = (int)min((long long)G, hack1 - h0);
+      const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
+      unsigned char *ring = smem_raw + (size_t)warp * STAGES * capw * 12;
+      uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)wpc * STAGES * capw * 12) + warp * STAGES;
+      const long long W = (long long)gridDim.x * wpc;
+      const long long first = hack0 + (long long)blockIdx.x * wpc + warp;
       const uint64_t pol_s = policy_evict_first();
       const uint64_t pol_x = policy_evict_last();
-      if (tid == 0) {
-            mbar_init(bar, 1);
+      if (lane == 0) {
+#pragma unroll
+            for (int s = 0; s < STAGES; ++s)
+                  mbar_init(&bars[s], 1);
             mbar_fence_init();
       }
-      for (int t = tid; t <= n; t += blockDim.x)
-            s_hoff[t] = hoff[h0 + t];
-      __syncthreads();
-      const long long s0 = s_hoff[0];
-      if (tid == 0) {
-            const long long cnt = s_hoff[n] - s0; // <= cap by the launcher's choice of G
-            mbar_expect_tx(bar, (uint32_t)(cnt * 12));
-            if (cnt > 0) {
-                  bulk_g2s(s_as, as + s0, (uint32_t)(cnt * 8), bar, pol_s);
-                  bulk_g2s(s_ja, ja + s0, (uint32_t)(cnt * 4), bar, pol_s);
+      __syncwarp();
+
+      long long b0[STAGES], b1[STAGES]; // slot range of the hack in flight in each stage
+      auto fetch = [&](int s) {         // lane 0: start the copies of stage s (b0/b1 already loaded)
+            if (lane == 0) {
+                  const long long cnt = b1[s] - b0[s];
+                  mbar_expect_tx(&bars[s], (uint32_t)(cnt * 12));
+                  if (cnt > 0) {
+                        bulk_g2s(ring + (size_t)s * capw * 12, as + b0[s], (uint32_t)(cnt * 8), &bars[s], pol_s);
+                        bulk_g2s(ring + (size_t)s * capw * 12 + (size_t)capw * 8, ja + b0[s], (uint32_t)(cnt * 4),
+                                 &bars[s], pol_s);
+                  }
+            }
+      };
+#pragma unroll
+      for (int s = 0; s < STAGES; ++s) {
+            const long long h = first + s * W;
+            b0[s] = b1[s] = 0;
+            if (h < hack1) {
+                  b0[s] = hoff[h], b1[s] = hoff[h + 1];
+                  fetch(s);
             }
       }
-      mbar_wait(bar, 0);
-
-      for (int i = warp; i < n; i += warps) {
-            const int base = (int)(s_hoff[i] - s0);
-            const int width = (int)((s_hoff[i + 1] - s_hoff[i]) >> 5);
-            const double *tas = s_as + base;
-            const int *tja = s_ja + base;
-            constexpr int U = 4;
-            double acc0 = 0.0, acc1 = 0.0;
-            for (int j = 0; j < width; j += U) {
-                  double a[U], xv[U];
-                  int c[U];
-                  bool okm[U];
+      for (long long i = 0;; i += STAGES) {
+            const uint32_t parity = (uint32_t)(i / STAGES) & 1u;
 #pragma unroll
-                  for (int u = 0; u < U; ++u) {
-                        const bool ok = j + u < width;
-                        okm[u] = ok;
-                        c[u] = ok ? tja[(j + u) * 32 + lane] : 0;
-                        a[u] = ok ? tas[(j + u) * 32 + lane] : 0.0;
+            for (int s = 0; s < STAGES; ++s) {
+                  const long long h = first + (i + s) * W;
+                  if (h >= hack1)
+                        return; // whole warp
+                  // offsets of the hack that takes this stage next: on their way while this one is computed
+                  const long long hn = h + STAGES * W;
+                  long long n0 = 0, n1 = 0;
+                  if (hn < hack1)
+                        n0 = hoff[hn], n1 = hoff[hn + 1];
+                  const int width = (int)((b1[s] - b0[s]) >> 5);
+                  mbar_wait(&bars[s], parity);
+                  const double *tas = reinterpret_cast<const double *>(ring + (size_t)s * capw * 12);
+                  const int *tja = reinterpret_cast<const int *>(ring + (size_t)s * capw * 12 + (size_t)capw * 8);
+                  constexpr int U = 8;
+                  double acc0 = 0.0, acc1 = 0.0;
+                  for (int j = 0; j < width; j += U) {
+                        double a[U], xv[U];
+                        int c[U];
+                        bool okm[U];
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                              const bool ok = j + u < width;
+                              okm[u] = ok;
+                              c[u] = ok ? tja[(j + u) * 32 + lane] : 0;
+                              a[u] = ok ? tas[(j + u) * 32 + lane] : 0.0;
+                        }
+#pragma unroll
+                        for (int u = 0; u < U; ++u)
+                              xv[u] = okm[u] ? ld_x(x + c[u], pol_x) : 0.0;
+#pragma unroll
+                        for (int u = 0; u < U; u += 2) {
+                              acc0 = fma(a[u], xv[u], acc0);
+                              acc1 = fma(a[u + 1], xv[u + 1], acc1);
+                        }
                   }
-#pragma unroll
-                  for (int u = 0; u < U; ++u)
-                        xv[u] = okm[u] ? ld_x(x + c[u], pol_x) : 0.0;
-#pragma unroll
-                  for (int u = 0; u < U; u += 2) {
-                        acc0 = fma(a[u], xv[u], acc0);
-                        acc1 = fma(a[u + 1], xv[u + 1], acc1);
-                  }
+                  __syncwarp(); // every lane has read the stage: it may be overwritten
+                  b0[s] = n0, b1[s] = n1;
+                  if (hn < hack1)
+                        fetch(s);
+                  double dot_acc = 0.0;
+                  const long long r = h * kHack + lane;
+                  if (r < M)
+                        store_y<EPI>(y, r, acc0 + acc1, epi, dot_acc);
+                  epi_finish_warp<EPI>(epi, dot_acc, h - hack0);
             }
-            double dot_acc = 0.0;
-            const long long r = (h0 + i) * kHack + lane;
-            if (r < M)
-                  store_y<EPI>(y, r, acc0 + acc1, epi, dot_acc);
-            epi_finish_warp<EPI>(epi, dot_acc, h0 + i - hack0);
       }
 }
 

@@ -32,7 +32,8 @@ extern Counters g_counters;
 struct Knobs {
       int csr_stream_cfg = -1; // -1: pick from warps_per_block and the row-length profile
       int hll_vec = -1;        // vector width of the HLL headline kernel; -1 = 1
-      int hll_block = -1;      // narrow hacks staged per CTA: -1 auto, 0 off, > 0 slots per CTA (forced)
+      int csr_pipe = -1;       // short regular CSR rows through per-warp bulk-copy rings: -1 auto, 0 off, 1 whenever they fit
+      int hll_pipe = -1;       // narrow hacks through per-warp bulk-copy rings: -1 auto, 0 off, 1 whenever they fit
       int hll_stream_cfg = -1;
       int regular_lpr = -1;    // force lanes-per-row (log2) of the adaptive base launch
       int force_wide = 0;      // use 64-bit row offsets even when NZ < 2^31 (tests)
@@ -56,9 +57,10 @@ extern Knobs g_knobs;
 
 extern int g_sm_count;
 constexpr int kMaxDevices = 64;
-// hll_block_kernel: hacks up to this width are staged per CTA, in groups of at most this many slots
-constexpr int kHllBlockMaxWidth = 12;
-constexpr int kHllBlockCap = 4096;
+// hll_pipe_kernel: matrices whose widest hack has at most this many slot columns
+constexpr int kHllPipeMaxWidth = 8;
+// csr_pipe_kernel: segments whose longest row has at most this many entries
+constexpr int kCsrPipeMaxRow = 8;
 
 int ensure_device();
 

@@ -925,6 +925,36 @@ int csr_ensure_sell(spmv_b200_csr *h) {
 // ================================================================== routing
 namespace b200 {
 
+static bool segment_max_row_at_most_8(const Segment &sg) {
+      static_assert(kKindMax[1] == kCsrPipeMaxRow, "bins 0 and 1 hold the rows of at most 8 entries");
+      for (int k = 2; k < kNumKinds; ++k)
+            if (sg.kind_rows[k])
+                  return false;
+      return sg.r1 > sg.r0;
+}
+
+// 0 launched, < 0 error
+template <typename OffT>
+static int launch_csr_pipe(const CsrArgs &a, long long r0, long long r1) {
+      constexpr int kStages = 2, kWarps = 8;
+      constexpr int capw = 32 * kCsrPipeMaxRow + 16; // a group's entries rounded out to multiples of 4
+      constexpr size_t smem = (size_t)kWarps * kStages * capw * 12 + (size_t)kWarps * kStages * 8;
+      auto kern = csr_pipe_kernel<kStages, OffT>;
+      static int occ_by_dev[kMaxDevices] = {0};
+      int &occ = occ_by_dev[a.h->device % kMaxDevices];
+      if (!occ) {
+            B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kWarps * 32, smem));
+            if (occ < 1)
+                  return fail(-EINVAL, "csr_pipe_kernel does not fit on an SM");
+      }
+      const long long groups = (r1 - r0 + 31) / 32;
+      const int g = (int)std::min<long long>((groups + kWarps - 1) / kWarps, (long long)occ * g_sm_count);
+      kern<<<g, kWarps * 32, smem, a.st>>>((const OffT *)a.h->d_irp, a.h->d_ja, a.h->d_as, r0, r1, capw, a.x, a.y);
+      ++g_counters.launches;
+      return 0;
+}
+
 constexpr long long kStreamDotSlots = 32768; // >= CTAs * consumer warps of any stream launch
 
 template <typename OffT>
@@ -957,6 +987,12 @@ static int run_kernel(spmv_b200_csr *h, int kernel, int wpb, Segment &sg, const 
             launch_block_rows<OffT>(a, sg.r0, sg.r1 - sg.r0, nullptr);
             return 0;
       case SPMV_B200_CSR_STREAM: {
+            // short regular rows: persistent warps with private bulk-copy rings (csr_pipe_kernel)
+            if (a.epi_mode == EPI_PLAIN && g_knobs.csr_pipe != 0 && g_knobs.csr_stream_cfg < 0 &&
+                segment_max_row_at_most_8(sg) &&
+                (g_knobs.csr_pipe > 0 || (sg.regular && sg.r1 - sg.r0 >= 32ll * 4 * g_sm_count * 8))) {
+                  return launch_csr_pipe<OffT>(a, sg.r0, sg.r1);
+            }
             const double mean_len = sg.r1 > sg.r0 ? (double)(h->h_irp[sg.r1] - h->h_irp[sg.r0]) /
                                                         (double)(sg.r1 - sg.r0)
                                                   : 0.0;
@@ -1694,31 +1730,38 @@ int hll_run_range(spmv_b200_hll *h, int kernel, int wpb, long long hack0, long l
             // and 128/64-bit variants, whose lanes share rows and split their gathers); the wide
             // variants stay selectable with the hll_vec knob.
             const int vec = g_knobs.hll_vec;
-            // narrow hacks: a CTA stages G consecutive hacks with two bulk copies (hll_block_kernel)
-            if (vec <= 1 && g_knobs.hll_block != 0 && h->max_width > 0 &&
-                (g_knobs.hll_block > 0 || h->max_width <= kHllBlockMaxWidth)) {
-                  const int cap = g_knobs.hll_block > 0 ? std::min(g_knobs.hll_block / 32 * 32, 16384) : kHllBlockCap;
-                  const int G = cap / (32 * h->max_width);
-                  if (G >= 8) {
-                        const size_t smem = (size_t)cap * 12 + ((size_t)G + 1) * 8 + 16;
-                        static size_t smem_set[2][kMaxDevices] = {{0}};
-                        const int fu = epi_mode == EPI_FUSED;
-                        if (smem_set[fu][h->device % kMaxDevices] < smem) {
-                              B200_CUDA(fu ? cudaFuncSetAttribute(hll_block_kernel<EPI_FUSED>,
-                                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                                           : cudaFuncSetAttribute(hll_block_kernel<EPI_PLAIN>,
-                                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                              smem_set[fu][h->device % kMaxDevices] = smem;
+            // narrow hacks: persistent warps, each with its own ring of bulk-copied hacks (hll_pipe_kernel)
+            if (vec <= 1 && g_knobs.hll_pipe != 0 && h->max_width > 0 && h->max_width <= kHllPipeMaxWidth &&
+                (g_knobs.hll_pipe > 0 || n >= 4ll * g_sm_count * 8)) {
+                  constexpr int kStages = 2, kWarps = 8;
+                  const int capw = 32 * kHllPipeMaxWidth;
+                  const size_t smem = (size_t)kWarps * kStages * capw * 12 + (size_t)kWarps * kStages * 8;
+                  const int fu = epi_mode == EPI_FUSED;
+                  static int occ_by_dev[2][kMaxDevices] = {{0}};
+                  int &occ = occ_by_dev[fu][h->device % kMaxDevices];
+                  if (!occ) {
+                        if (fu) {
+                              B200_CUDA(cudaFuncSetAttribute(hll_pipe_kernel<kStages, EPI_FUSED>,
+                                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                              B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                                  &occ, hll_pipe_kernel<kStages, EPI_FUSED>, kWarps * 32, smem));
+                        } else {
+                              B200_CUDA(cudaFuncSetAttribute(hll_pipe_kernel<kStages, EPI_PLAIN>,
+                                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                              B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                                  &occ, hll_pipe_kernel<kStages, EPI_PLAIN>, kWarps * 32, smem));
                         }
-                        const int g = (int)((n + G - 1) / G);
-                        if (fu)
-                              hll_block_kernel<EPI_FUSED><<<g, 256, smem, st>>>(h->d_hoff, h->d_ja, h->d_as, hack0, hack1,
-                                                                               G, cap, h->M, d_x, d_y, epi);
-                        else
-                              hll_block_kernel<EPI_PLAIN><<<g, 256, smem, st>>>(h->d_hoff, h->d_ja, h->d_as, hack0, hack1,
-                                                                               G, cap, h->M, d_x, d_y, epi);
-                        break;
+                        if (occ < 1)
+                              return fail(-EINVAL, "hll_pipe_kernel does not fit on an SM");
                   }
+                  const int g = (int)std::min<long long>((n + kWarps - 1) / kWarps, (long long)occ * g_sm_count);
+                  if (fu)
+                        hll_pipe_kernel<kStages, EPI_FUSED><<<g, kWarps * 32, smem, st>>>(
+                            h->d_hoff, h->d_ja, h->d_as, hack0, hack1, capw, h->M, d_x, d_y, epi);
+                  else
+                        hll_pipe_kernel<kStages, EPI_PLAIN><<<g, kWarps * 32, smem, st>>>(
+                            h->d_hoff, h->d_ja, h->d_as, hack0, hack1, capw, h->M, d_x, d_y, epi);
+                  break;
             }
             if (epi_mode == EPI_FUSED)
                   hll_warp_kernel<1, EPI_FUSED><<<grid, threads, 0, st>>>(
@@ -2136,7 +2179,8 @@ extern "C" int spmv_b200_set_knob(const char *key, int value) {
             int *slot;
       } table[] = {{"csr_stream_cfg", &g_knobs.csr_stream_cfg},
                    {"hll_vec", &g_knobs.hll_vec},
-                   {"hll_block", &g_knobs.hll_block},
+                   {"hll_pipe", &g_knobs.hll_pipe},
+                   {"csr_pipe", &g_knobs.csr_pipe},
                    {"hll_stream_cfg", &g_knobs.hll_stream_cfg},
                    {"regular_lpr", &g_knobs.regular_lpr},
                    {"force_wide", &g_knobs.force_wide},

@@ -127,3 +127,31 @@ def test_host_copy_pool(sp):
         L.spmv_b200_host_copy(C.c_void_p(dst.ctypes.data), C.c_void_p(src.ctypes.data), src.nbytes)
     gbs = 5 * src.nbytes / (time.perf_counter() - t0) / 1e9
     assert gbs > 1.0
+
+
+def test_host_copy_pool_with_a_pinned_caller():
+    """OMP_PROC_BIND (set by bench.py for the CPU baseline) binds the initial thread to one CPU and
+    threads created later inherit that mask; the copy team takes the CPUs the container allows
+    instead, so a pinned caller must not put the whole team on one core (measured on the bench box
+    before the fix: 3.5 s per 2 GiB pass)."""
+    import subprocess
+    import sys
+    code = r'''
+import os, ctypes as C, time, numpy as np
+os.sched_setaffinity(0, {sorted(os.sched_getaffinity(0))[0]})
+import spmv_scpa_b200 as sp
+L = sp._lib.b200
+src = np.random.default_rng(0).integers(0, 255, 64 << 20, dtype=np.uint8); dst = np.zeros_like(src)
+L.spmv_b200_host_copy(C.c_void_p(dst.ctypes.data), C.c_void_p(src.ctypes.data), src.nbytes)
+t0 = time.perf_counter()
+for _ in range(4):
+    L.spmv_b200_host_copy(C.c_void_p(dst.ctypes.data), C.c_void_p(src.ctypes.data), src.nbytes)
+gbs = 4 * src.nbytes / (time.perf_counter() - t0) / 1e9
+assert np.array_equal(src, dst)
+print("GBS", gbs)
+'''
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    gbs = float(out.stdout.split("GBS")[1])
+    assert gbs > 1.0, gbs

@@ -422,22 +422,24 @@ def test_fused_axpby_dot(sp, O, torch, name):
         sp.set_knob("sell_chunk", 256)
 
 
-def test_hll_block_staged_kernel(sp, O, torch):
-    """HLL id 2 on narrow hacks: a CTA stages a group of consecutive hacks with two bulk copies
-    (hll_block_kernel).  Same y as the reference serial CSR for every group size, with empty hacks,
-    hacks of different widths, a last group that is cut short, hack ranges (the host-buffer
-    pipeline's launches) and wide matrices that must stay on the warp-per-hack kernel."""
+def test_hll_pipelined_narrow_hacks(sp, O, torch):
+    """HLL id 2 on narrow hacks: persistent warps, each with its own ring of bulk-copied hacks
+    (hll_pipe_kernel).  Same y as the reference serial CSR with empty hacks, hacks of different
+    widths, fewer hacks than warps, hack ranges (the host-buffer pipeline's launches), the fused
+    epilogue; matrices with a wider hack stay on the warp-per-hack kernel."""
     rng = np.random.default_rng(21)
-    M, N = 32 * 211 + 13, 5000
-    lens = rng.integers(0, 11, M)
-    lens[32 * 40:32 * 44] = 0                                 # four empty hacks
-    lens[32 * 100:32 * 101] = 1
-    IRP = np.zeros(M + 1, np.int32)
-    IRP[1:] = np.cumsum(lens)
-    JA = np.concatenate([np.sort(rng.choice(N, l, replace=False)) for l in lens]).astype(np.int32)
-    AS = rng.uniform(-1, 1, JA.size)
-    cases = [("narrow", sp.csr_from_arrays("narrow", M, N, IRP, JA, AS)), ("poisson", sp.gen_poisson2d(123, 77)),
-             ("stencil27", sp.gen_stencil27(14, 13, 12))]
+    cases = []
+    for M in (32 * 211 + 13, 32 * 9000 + 5, 40):
+        N = 5000
+        lens = rng.integers(0, 9, M)
+        lens[32 * 40:32 * 44] = 0                             # four empty hacks
+        lens[32 * 100:32 * 101] = 1
+        IRP = np.zeros(M + 1, np.int32)
+        IRP[1:] = np.cumsum(lens)
+        JA = np.concatenate([np.sort(rng.choice(N, l, replace=False)) for l in lens] + [np.zeros(0, np.int64)]).astype(np.int32)
+        AS = rng.uniform(-1, 1, JA.size)
+        cases.append((f"narrow{M}", sp.csr_from_arrays("narrow", M, N, IRP, JA, AS)))
+    cases += [("poisson", sp.gen_poisson2d(640, 333)), ("stencil27", sp.gen_stencil27(14, 13, 12))]
     try:
         for name, A in cases:
             irp, ja, as_ = A.IRP.copy(), A.JA.copy(), A.AS.copy()
@@ -445,20 +447,79 @@ def test_hll_block_staged_kernel(sp, O, torch):
             y_ref = O.csr_spmv(A.M, irp, ja, as_, x)
             bound = O.csr_abs_bound(A.M, irp, ja, as_, x)
             xd = dev(torch, x)
-            for block in (-1, 0, 512, 1024, 4096, 16384):
-                sp.set_knob("hll_block", block)
+            got = {}
+            for pipe in (0, 1, -1):
+                sp.set_knob("hll_pipe", pipe)
                 for h in (sp.CsrDevice.from_host(A).to_hll(), sp.HllDevice.from_host(sp.csr_to_hll(A, True))):
                     y = torch.full((A.M,), float("nan"), dtype=torch.float64, device="cuda")
                     h.spmv(xd, y, kernel=2, warps_per_block=4)
-                    ok, worst = O.check_tolerance(y.cpu().numpy(), y_ref, bound, TOL)
-                    assert ok, (name, block, worst)
+                    got[pipe] = y.cpu().numpy()
+                    ok, worst = O.check_tolerance(got[pipe], y_ref, bound, TOL)
+                    assert ok, (name, pipe, worst)
                     yh = np.full(A.M, np.nan)
                     h.spmv_host(x, yh, kernel=2)              # launches on hack ranges
                     ok, worst = O.check_tolerance(yh, y_ref, bound, TOL)
-                    assert ok, (name, block, "host", worst)
+                    assert ok, (name, pipe, "host", worst)
+                    dot = torch.zeros(1, dtype=torch.float64, device="cuda")
+                    h.spmv_fused(xd, y, 2.0, 0.0, None, y, dot, kernel=2)
+                    assert np.array_equal(y.cpu().numpy(), 2.0 * got[pipe])
+                    h.close()
+            # lane = row and the same summation order in both kernels: bit-identical
+            assert np.array_equal(got[0], got[1])
+    finally:
+        sp.set_knob("hll_pipe", -1)
+
+
+def test_csr_pipelined_short_rows(sp, O, torch):
+    """CSR ids 2 / 4 on short rows (<= 8 entries): persistent warps with private rings of bulk-copied
+    row groups (csr_pipe_kernel).  Same y as the reference serial CSR with empty rows, a ragged last
+    group, row-range launches on cut handles, 64-bit row offsets and the host-buffer pass."""
+    rng = np.random.default_rng(22)
+    cases = []
+    for M in (32 * 211 + 13, 32 * 9000 + 5, 7):
+        N = 5000
+        lens = rng.integers(0, 9, M)
+        lens[32 * 40:32 * 44] = 0
+        IRP = np.zeros(M + 1, np.int32)
+        IRP[1:] = np.cumsum(lens)
+        JA = np.concatenate([np.sort(rng.choice(N, l, replace=False)) for l in lens] + [np.zeros(0, np.int64)]).astype(np.int32)
+        cases.append((M, N, IRP, JA, rng.uniform(-1, 1, JA.size)))
+    P = sp.gen_poisson2d(640, 333)
+    cases.append((P.M, P.N, P.IRP.copy(), P.JA.copy(), P.AS.copy()))
+    try:
+        for M, N, IRP, JA, AS in cases:
+            x = rng.uniform(-1, 1, N)
+            y_ref = O.csr_spmv(M, IRP, JA, AS, x)
+            bound = O.csr_abs_bound(M, IRP, JA, AS, x)
+            xd = dev(torch, x)
+            cut = (M // 3) // 32 * 32 + 5
+            for pipe in (1, -1, 0):
+                sp.set_knob("csr_pipe", pipe)
+                for wide in (0, 1):
+                    sp.set_knob("force_wide", wide)
+                    h = sp.CsrDevice.from_arrays(M, N, IRP.astype(np.int64) if wide else IRP, JA, AS,
+                                                 cuts=(cut,) if M > 100 else ())
+                    sp.set_knob("force_wide", 0)
+                    for kernel in (2, 4):
+                        y = torch.full((M,), float("nan"), dtype=torch.float64, device="cuda")
+                        h.spmv(xd, y, kernel=kernel)
+                        ok, worst = O.check_tolerance(y.cpu().numpy(), y_ref, bound, TOL)
+                        assert ok, (M, pipe, wide, kernel, worst)
+                    if M > 100:                               # the two segments one after the other
+                        y = torch.full((M,), float("nan"), dtype=torch.float64, device="cuda")
+                        h.spmv(xd, y, kernel=2, rows=(cut, M))
+                        assert torch.isnan(y[:cut]).all()
+                        h.spmv(xd, y, kernel=2, rows=(0, cut))
+                        ok, worst = O.check_tolerance(y.cpu().numpy(), y_ref, bound, TOL)
+                        assert ok, (M, pipe, wide, "ranges", worst)
+                    yh = np.full(M, np.nan)
+                    h.spmv_host(x, yh, kernel=2)
+                    ok, worst = O.check_tolerance(yh, y_ref, bound, TOL)
+                    assert ok, (M, pipe, wide, "host", worst)
                     h.close()
     finally:
-        sp.set_knob("hll_block", -1)
+        sp.set_knob("csr_pipe", -1)
+        sp.set_knob("force_wide", 0)
 
 
 def test_handle_host_spmv(sp, O, torch):

@@ -395,6 +395,11 @@ int main(int argc, char **argv) {
             }
             for (int w = 0; w < 4; ++w)
                   run_csr(&c, h, 2, wpbs[w], "auto");
+            spmv_b200_set_knob("csr_pipe", 0); /* short regular rows: without the per-warp rings */
+            run_csr(&c, h, 2, 4, "pipe=0");
+            spmv_b200_set_knob("csr_pipe", 1);
+            run_csr(&c, h, 2, 4, "pipe=1");
+            spmv_b200_set_knob("csr_pipe", -1);
             spmv_b200_set_knob("adaptive_direct", 1);
             for (int w = 0; w < 3; ++w)
                   run_csr(&c, h, 2, wpbs[w], "direct-binned");
@@ -443,7 +448,7 @@ int main(int argc, char **argv) {
                    100.0 * (spmv_b200_hll_slots(hh) - (double)A->NZ) / (A->NZ ? A->NZ : 1));
             for (int w = 0; w < 4; ++w)
                   run_hll(&c, hh, 1, wpbs[w], "-");
-            spmv_b200_set_knob("hll_block", 0); /* warp per hack, whatever the width */
+            spmv_b200_set_knob("hll_pipe", 0); /* warp per hack, whatever the width */
             for (int v = 1; v <= 4; v *= 2) {
                   spmv_b200_set_knob("hll_vec", v);
                   snprintf(knob, sizeof knob, "vec=%d", v);
@@ -451,16 +456,12 @@ int main(int argc, char **argv) {
                         run_hll(&c, hh, 2, wpbs[w], knob);
             }
             spmv_b200_set_knob("hll_vec", -1);
-            /* hacks staged per CTA (bulk copies): what the library picks, then forced group sizes */
-            spmv_b200_set_knob("hll_block", -1);
-            run_hll(&c, hh, 2, 4, "block=auto");
-            static const int caps[] = {1024, 2048, 4096, 8192, 16384};
-            for (int i = 0; i < 5; ++i) {
-                  spmv_b200_set_knob("hll_block", caps[i]);
-                  snprintf(knob, sizeof knob, "block=%d", caps[i]);
-                  run_hll(&c, hh, 2, 4, knob);
-            }
-            spmv_b200_set_knob("hll_block", -1);
+            /* narrow hacks: persistent warps with private bulk-copy rings (what id 2 picks for them) */
+            spmv_b200_set_knob("hll_pipe", -1);
+            run_hll(&c, hh, 2, 4, "pipe=auto");
+            spmv_b200_set_knob("hll_pipe", 1);
+            run_hll(&c, hh, 2, 4, "pipe=1");
+            spmv_b200_set_knob("hll_pipe", -1);
             for (int cfg = 0; cfg < 3; ++cfg) {
                   spmv_b200_set_knob("hll_stream_cfg", cfg);
                   snprintf(knob, sizeof knob, "cfg=%d", cfg);
