@@ -282,6 +282,11 @@ KERNEL_SYMBOL = {("csr", 0): "csr_vec_kernel<1,", ("csr", 1): "csr_vec_kernel<32
                  ("hll", 3): "hll_stream_kernel"}
 
 
+# what ids 2 of each format resolve to on the BASELINE configs (profiles/r2_*_ncu_summary.md)
+DOMINANT_KERNEL = {("c1", "csr"): "csr_pipe_kernel", ("c1", "hll"): "hll_pipe_kernel",
+                   ("c3", "csr"): "sell_kernel", ("c3", "hll"): "sell_kernel", ("c4", "csr"): "sell_kernel"}
+
+
 def single_config(sp, O, torch, workload, steps, warmup, wpb, with_cpu=True, with_e2e=True, kernels=None):
     """One BASELINE single-GPU config: parity gate, then device-timed CSR and HLL, the e2e entry
     points and the reference's CPU paths on the same matrix."""
@@ -348,7 +353,7 @@ def single_config(sp, O, torch, workload, steps, warmup, wpb, with_cpu=True, wit
                "gbs": bmin / (ms_step * 1e6), "launches_per_step": launches // steps,
                "roofline": {"bound": "hbm", "achieved": bmin / (kern_ms * 1e6), "peak": peak, "unit": "GB/s",
                             "frac": bmin / (kern_ms * 1e6) / peak, "frac_of_8TBs": bmin / (kern_ms * 1e6) / 8000.0,
-                            "traffic": ncu_traffic(workload, KERNEL_SYMBOL[(name, k)]),
+                            "traffic": ncu_traffic(workload, DOMINANT_KERNEL.get((workload, name), KERNEL_SYMBOL[(name, k)])),
                             "peak_source": peak_src, "kernel_ms_mean": kern_ms, "kernel_ms_min": min(per),
                             "algorithmic_bytes": bmin}}
         if name == "csr":
@@ -440,6 +445,7 @@ def single_config(sp, O, torch, workload, steps, warmup, wpb, with_cpu=True, wit
            "parity": parity, "formats": results, "e2e": e2e, "cpu_baseline": cpu,
            "wall_s": time.time() - t_start}
     del A
+    progress(f"config {workload} done in {rec['wall_s']:.1f} s")
     return rec
 
 
@@ -489,6 +495,15 @@ def run_single(args):
     }
     emit(line)
     return 0
+
+
+_T_START = time.time()
+
+
+def progress(msg):
+    """Phase marker on stderr (stdout carries the one JSON line)."""
+    sys.stderr.write(f"[bench +{time.time() - _T_START:6.1f}s] {msg}\n")
+    sys.stderr.flush()
 
 
 def emit(line):

@@ -51,7 +51,7 @@ def gather_lists(dist, torch, device, values):
 def run(args):
     import torch
     import torch.distributed as dist
-    from bench import (ClockSampler, DESCR, emit, host_cores, measured_peak, ncu_traffic, roofline_bytes,
+    from bench import (ClockSampler, DESCR, emit, host_cores, measured_peak, ncu_traffic, progress, roofline_bytes,
                        reference_gpu_rows, single_config, cpu_reference_run)
 
     rank = int(os.environ.get("RANK", "0"))
@@ -147,6 +147,8 @@ def run(args):
         dist.barrier()
     launches = sp.counters()["launches"] - launches0
     clocks = sampler.stop(t_region0, time.time()) if sampler else None
+    if rank == 0:
+        progress(f"{args.workload}: {len(region_ms_mine)} timed regions done")
     by_rank = gather_lists(dist, torch, device, region_ms_mine)          # [rank][region]
     region_ms = [max(by_rank[r][i] for r in range(world)) for i in range(len(region_ms_mine))]
     total_ms = statistics.median(region_ms)
@@ -252,6 +254,8 @@ def run(args):
     torch.cuda.synchronize()
     dist.barrier()
 
+    if rank == 0:
+        progress("stand-alone kernel, parity and e2e done")
     # ---- N = 1 extras: CPU baseline (bounded sample), the single-GPU BASELINE configs, and the
     #      reference's own CUDA kernels on this GPU ----
     if rank == 0 and world == 1:

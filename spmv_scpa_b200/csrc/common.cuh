@@ -208,6 +208,9 @@ __device__ __forceinline__ double group_sum(double v) {
 //              or peer access, reached over NVLink): the multi-GPU halo
 //              exchange fused into the SpMV epilogue
 //   EPI_ACC    y[row] += v  (column panels after the first one)
+//   EPI_ACC_PUSH  y[row] += v, and the finished sum goes to the peers like EPI_PUSH (last column
+//              panel of a shard whose next x slice every peer needs: the all-gather of a general
+//              matrix fused into the SpMV epilogue)
 //   EPI_FUSED  y[row] = alpha*v + beta*z[row], and sum_i y[i]*w[i] is
 //              accumulated per warp (iterated solvers: SpMV + axpby + dot in
 //              one pass over the matrix)
@@ -215,12 +218,14 @@ constexpr int EPI_PLAIN = 0;
 constexpr int EPI_PUSH = 1;
 constexpr int EPI_ACC = 2;
 constexpr int EPI_FUSED = 3;
+constexpr int EPI_ACC_PUSH = 4;
+constexpr int kMaxPush = 8; // peers one launch can store to (7 = every other GPU of an 8-GPU box)
 
 struct EpiArgs {
       // EPI_PUSH
       int n_push;
-      long long row0[2], row1[2];
-      double *dst[2];
+      long long row0[kMaxPush], row1[kMaxPush];
+      double *dst[kMaxPush];
       // EPI_FUSED (z, w, dot_partial may be null)
       double alpha, beta;
       const double *z, *w;
@@ -240,11 +245,12 @@ __device__ __forceinline__ void store_y(double *y, long long row, double v, cons
             if (e.w)
                   dot_acc = fma(r, e.w[row], dot_acc);
       } else {
+            if (EPI == EPI_ACC_PUSH)
+                  v += y[row];
             y[row] = v;
-            if (EPI == EPI_PUSH) {
-#pragma unroll
-                  for (int i = 0; i < 2; ++i)
-                        if (i < e.n_push && row >= e.row0[i] && row < e.row1[i])
+            if (EPI == EPI_PUSH || EPI == EPI_ACC_PUSH) {
+                  for (int i = 0; i < e.n_push; ++i)
+                        if (row >= e.row0[i] && row < e.row1[i])
                               e.dst[i][row - e.row0[i]] = v;
             }
       }

@@ -579,8 +579,9 @@ __global__ void __launch_bounds__(256)
                   hi = k_hi;
             k_lo = __shfl_sync(0xffffffffu, lo, 0);
       };
-      int s0[STAGES], s1[STAGES]; // this lane's entries inside the stage's buffer
+      int s0[STAGES] = {0}, s1[STAGES] = {0}; // this lane's entries inside the stage's buffer
       auto fetch = [&](int s, long long lo, long long hi, long long k_lo, long long k_hi) {
+            // (rounding out to 128-byte lines instead measured the same: profiles/r2_kbench_poisson3000_pipe.txt)
             const long long ka = k_lo & ~3ll, kb = (k_hi + 3) & ~3ll;
             s0[s] = (int)(lo - ka), s1[s] = (int)(hi - ka);
             if (lane == 0) {

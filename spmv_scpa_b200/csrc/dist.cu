@@ -206,11 +206,12 @@ extern "C" int spmv_b200_dist_make_plan(int rank, int world, const spmv_b200_sha
             return fail(-EINVAL, "dist_make_plan: bad arguments (at most %d ranks)",
                         SPMV_B200_MAX_RANKS);
       // the mode must be the same on every rank: decide it from everybody's plan
-      bool push_ok = true, all_gather = world > 1, equal = true, covered = true;
+      bool all_gather = world > 1, equal = true, covered = true;
+      int targets = 0; // most peers any boundary segment stores to
       for (int q = 0; q < world; ++q) {
             spmv_b200_dist_plan pq;
             plan_one(q, world, table, &pq);
-            push_ok = push_ok && max_push_targets(pq, table[q]) <= 2;
+            targets = std::max(targets, max_push_targets(pq, table[q]));
             covered = covered && pq.covered;
             all_gather = all_gather && table[q].c0 == table[0].r0 && table[q].c1 == table[world - 1].r1;
             equal = equal && table[q].r1 - table[q].r0 == table[0].r1 - table[0].r0 &&
@@ -220,11 +221,19 @@ extern "C" int spmv_b200_dist_make_plan(int rank, int world, const spmv_b200_sha
             return fail(-EINVAL, "dist_make_plan: row ranges do not tile the needed column ranges");
       plan_one(rank, world, table, out);
       out->all_gather = all_gather && equal;
-      if (want_mode == SPMV_B200_DIST_PUSH && !push_ok)
-            return fail(-EINVAL, "dist_make_plan: this partition needs more than two push targets "
-                                 "per boundary segment; use SPMV_B200_DIST_NCCL or _AUTO");
-      out->mode = want_mode == SPMV_B200_DIST_AUTO ? (push_ok ? SPMV_B200_DIST_PUSH : SPMV_B200_DIST_NCCL)
-                                                   : want_mode;
+      if (want_mode == SPMV_B200_DIST_PUSH && targets > kMaxPush)
+            return fail(-EINVAL, "dist_make_plan: this partition needs more than %d push targets "
+                                 "per boundary segment; use SPMV_B200_DIST_NCCL or _AUTO", kMaxPush);
+      // AUTO: halo plans (at most two peers per boundary segment) push.  Plans in which a segment
+      // feeds more peers -- a general matrix: every peer needs every slice -- push as well (the
+      // all-gather fused into the SpMV epilogue, stores to up to 7 peers over NVLink) unless
+      // SPMV_B200_PUSH_ALL=0 sends them through the NCCL exchange.
+      bool push = targets <= 2;
+      if (!push && targets <= kMaxPush) {
+            const char *env = getenv("SPMV_B200_PUSH_ALL");
+            push = !(env && !strcmp(env, "0"));
+      }
+      out->mode = want_mode == SPMV_B200_DIST_AUTO ? (push ? SPMV_B200_DIST_PUSH : SPMV_B200_DIST_NCCL) : want_mode;
       return 0;
 }
 
@@ -407,6 +416,9 @@ struct Peer {
       int64_t c0 = 0;
 };
 constexpr size_t kCtlBytes = 4096;
+// all-gather plans: the step's rows become final in up to this many blocks, each handed to the
+// copy engines while the later ones still compute
+constexpr int kGatherBlocks = 4;
 
 } // namespace
 
@@ -433,6 +445,9 @@ struct spmv_b200_dist {
       std::vector<Seg> segs;
       cudaStream_t st = nullptr, comm = nullptr;
       cudaEvent_t ev_b = nullptr, ev_done = nullptr;
+      cudaEvent_t ev_blk[kGatherBlocks] = {nullptr}; // all-gather by copy engines: one per finished row block
+      cudaStream_t peer_st[kMaxPush] = {nullptr};    // ... one stream per target, so that the copies to
+      cudaEvent_t peer_done[kMaxPush] = {nullptr};   //     different peers run on different copy engines
       cudaGraphExec_t graph = nullptr;
       bool graph_failed = false, connected = false;
       int eager_steps = 0;
@@ -446,6 +461,16 @@ struct spmv_b200_dist {
 namespace {
 
 double *own(spmv_b200_dist *d, int buf) { return d->X[buf] + d->own0; }
+
+// row blocks per step of an all-gather plan (SPMV_B200_GATHER_BLOCKS = 1 .. kGatherBlocks)
+int gather_blocks() {
+      static int n = 0;
+      if (!n) {
+            const char *env = getenv("SPMV_B200_GATHER_BLOCKS");
+            n = env && atoi(env) > 0 ? std::min(atoi(env), kGatherBlocks) : 2; // C3 at 8 GPUs: 1 / 2 / 4 blocks -> 0.744 / 0.659 / 0.696 ms
+      }
+      return n;
+}
 
 int nccl_exchange(spmv_b200_dist *d, int buf, cudaStream_t st) {
       const spmv_b200_dist_plan &P = d->plan;
@@ -479,8 +504,8 @@ int push_args_for(spmv_b200_dist *d, const Seg &sg, int dst, EpiArgs *out) {
                           b = std::min(P.send[i].g1 - d->me.r0, sg.r1);
             if (a >= b)
                   continue;
-            if (out->n_push >= 2)
-                  return fail(-EINVAL, "push epilogue supports two peers per boundary segment");
+            if (out->n_push >= kMaxPush)
+                  return fail(-EINVAL, "push epilogue supports %d peers per boundary segment", kMaxPush);
             const Peer &pr = d->peers[P.send[i].peer];
             out->row0[out->n_push] = a;
             out->row1[out->n_push] = b;
@@ -509,6 +534,54 @@ int dist_step(spmv_b200_dist *d, int phase = 0) {
                         continue;
                   EpiArgs e;
                   int rc = push_args_for(d, sg, dst, &e);
+                  if (!rc && e.n_push > 2 && sg.r0 == 0 && sg.r1 == d->M) {
+                        // A general matrix: every peer needs this rank's whole next slice.  Stores
+                        // from the epilogue would leave as 8-byte writes in the row order of the
+                        // sorted slices / row lists (measured at 8 GPUs on C3: 14 M remote writes
+                        // per GPU and step, 1.28 ms against 0.83 ms through NCCL), so the finished
+                        // row blocks go out as peer copies on the copy engines instead, block b
+                        // travelling while block b+1 computes; the shard keeps its best
+                        // single-GPU route (column panels, virtual rows).
+                        int nb = 0;
+                        cudaError_t ce = cudaSuccess;
+                        for (int i = 0; i < e.n_push && ce == cudaSuccess; ++i)
+                              if (!d->peer_st[i]) {
+                                    int lo_p = 0, hi_p = 0;
+                                    cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p);
+                                    ce = cudaStreamCreateWithPriority(&d->peer_st[i], cudaStreamNonBlocking, hi_p);
+                                    if (ce == cudaSuccess)
+                                          ce = cudaEventCreateWithFlags(&d->peer_done[i], cudaEventDisableTiming);
+                              }
+                        auto done = [&](long long a, long long b) {
+                              if (nb >= kGatherBlocks || a >= b)
+                                    return;
+                              cudaEvent_t ev = d->ev_blk[nb++];
+                              if (ce == cudaSuccess)
+                                    ce = cudaEventRecord(ev, st);
+                              for (int i = 0; i < e.n_push && ce == cudaSuccess; ++i) {
+                                    const long long lo = std::max<long long>(a, e.row0[i]),
+                                                    hi = std::min<long long>(b, e.row1[i]);
+                                    if (lo >= hi)
+                                          continue;
+                                    ce = cudaStreamWaitEvent(d->peer_st[i], ev, 0);
+                                    if (ce == cudaSuccess)
+                                          ce = cudaMemcpyAsync(e.dst[i] + (lo - e.row0[i]), y + lo,
+                                                               (size_t)(hi - lo) * sizeof(double),
+                                                               cudaMemcpyDeviceToDevice, d->peer_st[i]);
+                              }
+                        };
+                        rc = ce == cudaSuccess ? csr_run_blocks(d->shard, d->kernel, d->wpb, x, y, st, gather_blocks(), done)
+                                               : -EIO;
+                        if (ce != cudaSuccess)
+                              rc = fail(-EIO, "all-gather copies failed: %s", cudaGetErrorString(ce));
+                        for (int i = 0; i < e.n_push && !rc && nb > 0; ++i) { // join: the signal follows the last copy
+                              B200_CUDA(cudaEventRecord(d->peer_done[i], d->peer_st[i]));
+                              B200_CUDA(cudaStreamWaitEvent(st, d->peer_done[i], 0));
+                        }
+                        if (rc)
+                              return rc;
+                        continue;
+                  }
                   rc = rc ? rc : csr_run(d->shard, d->kernel, d->wpb, sg.r0, sg.r1, x, y,
                                          e.n_push ? EPI_PUSH : EPI_PLAIN, e, st);
                   if (rc)
@@ -668,6 +741,8 @@ extern "C" spmv_b200_dist *spmv_b200_dist_create(const spmv_b200_dist_plan *plan
            cudaStreamCreateWithPriority(&d->comm, cudaStreamNonBlocking, hi) == cudaSuccess &&
            cudaEventCreateWithFlags(&d->ev_b, cudaEventDisableTiming) == cudaSuccess &&
            cudaEventCreateWithFlags(&d->ev_done, cudaEventDisableTiming) == cudaSuccess;
+      for (int i = 0; i < kGatherBlocks; ++i)
+            ok = ok && cudaEventCreateWithFlags(&d->ev_blk[i], cudaEventDisableTiming) == cudaSuccess;
       if (!ok) {
             fail(-ENOMEM, "dist_create: %s", cudaGetErrorString(cudaGetLastError()));
             spmv_b200_dist_destroy(d);
@@ -878,6 +953,17 @@ extern "C" void spmv_b200_dist_destroy(spmv_b200_dist *d) {
             cudaEventDestroy(d->ev_b);
       if (d->ev_done)
             cudaEventDestroy(d->ev_done);
+      for (cudaEvent_t e : d->ev_blk)
+            if (e)
+                  cudaEventDestroy(e);
+      for (int i = 0; i < kMaxPush; ++i) {
+            if (d->peer_st[i]) {
+                  cudaStreamSynchronize(d->peer_st[i]);
+                  cudaStreamDestroy(d->peer_st[i]);
+            }
+            if (d->peer_done[i])
+                  cudaEventDestroy(d->peer_done[i]);
+      }
       if (d->st)
             cudaStreamDestroy(d->st);
       if (d->comm)

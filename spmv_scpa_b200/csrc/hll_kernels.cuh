@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(256)
       }
       __syncwarp();
 
-      long long b0[STAGES], b1[STAGES]; // slot range of the hack in flight in each stage
+      long long b0[STAGES] = {0}, b1[STAGES] = {0}; // slot range of the hack in flight in each stage
       auto fetch = [&](int s) {         // lane 0: start the copies of stage s (b0/b1 already loaded)
             if (lane == 0) {
                   const long long cnt = b1[s] - b0[s];

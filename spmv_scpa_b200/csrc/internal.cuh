@@ -8,6 +8,7 @@
 #include <cerrno>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <numeric>
@@ -216,6 +217,8 @@ int csr_run_segment(spmv_b200_csr *h, Segment &sg, int kernel, int wpb, const do
                     double *d_y, int epi_mode, const EpiArgs &epi, cudaStream_t st);
 int csr_run(spmv_b200_csr *h, int kernel, int wpb, long long row0, long long row1,
             const double *d_x, double *d_y, int epi_mode, const EpiArgs &epi, void *stream);
+int csr_run_blocks(spmv_b200_csr *h, int kernel, int wpb, const double *d_x, double *d_y, void *stream,
+                   int blocks, const std::function<void(long long, long long)> &done);
 int hll_run_range(spmv_b200_hll *h, int kernel, int wpb, long long hack0, long long hack1,
                   const double *d_x, double *d_y, int epi_mode, const EpiArgs &epi, void *stream);
 double median_of(std::vector<double> v);

@@ -801,7 +801,8 @@ int launch_sell_hot_any(const SellPlan &sp, const double *d_x, double *d_y, cons
 }
 
 int sell_run(const SellPlan &sp, int wpb, const double *d_x, double *d_y, int epi_mode,
-             const EpiArgs &epi, cudaStream_t st) {
+             const EpiArgs &epi, cudaStream_t st, int blocks = 0,
+             const std::function<void(long long, long long)> *block_done = nullptr) {
       const int threads = 32 * wpb;
       const int grid = blocks_for(sp.n_slices * 32, threads);
       const bool u8 = g_knobs.sell_unroll == 8;
@@ -836,25 +837,44 @@ int sell_run(const SellPlan &sp, int wpb, const double *d_x, double *d_y, int ep
             }
             return 0;
       }
-      for (int p = 0; p < sp.K; ++p) {
-            const long long *soff = sp.d_soff + (size_t)p * (sp.n_slices + 1);
-            const int *perm = sp.d_perm + (size_t)p * sp.n_slices * 32;
-            if (p > 0 && u8)
-                  sell_kernel<EPI_ACC, 8><<<grid, threads, 0, st>>>(soff, perm, sp.d_ja, sp.d_as,
-                                                                    sp.n_slices, d_x, d_y, nullptr, epi);
+      // The last panel may run as `blocks` launches over runs of whole windows, `block_done(r0, r1)`
+      // called after each: rows [r0, r1) of y are final from then on in stream order (rows never
+      // leave their window).  The multi-GPU all-gather sends finished blocks while later ones compute.
+      const int n_blocks = block_done && blocks ? std::max(1, blocks) : 1;
+      const long long win_slices = std::max<long long>(1, sp.sigma / 32);
+      const long long n_win = (sp.n_slices + win_slices - 1) / win_slices;
+      for (int p = 0; p < sp.K; ++p)
+            for (int b = 0; b < (p == sp.K - 1 ? n_blocks : 1); ++b) {
+            const bool last = p == sp.K - 1;
+            const long long s0 = last ? std::min(sp.n_slices, n_win * b / n_blocks * win_slices) : 0;
+            const long long s1 = last ? std::min(sp.n_slices, n_win * (b + 1) / n_blocks * win_slices) : sp.n_slices;
+            if (s1 <= s0)
+                  continue;
+            const long long *soff = sp.d_soff + (size_t)p * (sp.n_slices + 1) + s0;
+            const int *perm = sp.d_perm + ((size_t)p * sp.n_slices + s0) * 32;
+            const long long ns = s1 - s0;
+            const int grid = blocks_for(ns * 32, threads);
+            const bool push = epi_mode == EPI_PUSH && last; // finished sums also go to the peers
+#define SELL_LAUNCH(E, U)                                                                          \
+      sell_kernel<E, U><<<grid, threads, 0, st>>>(soff, perm, sp.d_ja, sp.d_as, ns, d_x, d_y, nullptr, epi)
+            if (push && p > 0)
+                  SELL_LAUNCH(EPI_ACC_PUSH, 4);
+            else if (push)
+                  SELL_LAUNCH(EPI_PUSH, 4);
+            else if (p > 0 && u8)
+                  SELL_LAUNCH(EPI_ACC, 8);
             else if (p > 0)
-                  sell_kernel<EPI_ACC, 4><<<grid, threads, 0, st>>>(soff, perm, sp.d_ja, sp.d_as,
-                                                                    sp.n_slices, d_x, d_y, nullptr, epi);
+                  SELL_LAUNCH(EPI_ACC, 4);
             else if (epi_mode == EPI_FUSED)
-                  sell_kernel<EPI_FUSED, 4><<<grid, threads, 0, st>>>(soff, perm, sp.d_ja, sp.d_as,
-                                                                      sp.n_slices, d_x, d_y, nullptr, epi);
+                  SELL_LAUNCH(EPI_FUSED, 4);
             else if (u8)
-                  sell_kernel<EPI_PLAIN, 8><<<grid, threads, 0, st>>>(soff, perm, sp.d_ja, sp.d_as,
-                                                                      sp.n_slices, d_x, d_y, nullptr, epi);
+                  SELL_LAUNCH(EPI_PLAIN, 8);
             else
-                  sell_kernel<EPI_PLAIN, 4><<<grid, threads, 0, st>>>(soff, perm, sp.d_ja, sp.d_as,
-                                                                      sp.n_slices, d_x, d_y, nullptr, epi);
+                  SELL_LAUNCH(EPI_PLAIN, 4);
+#undef SELL_LAUNCH
             ++g_counters.launches;
+            if (last && block_done && blocks)
+                  (*block_done)(s0 * 32, std::min(sp.M, s1 * 32));
       }
       return 0;
 }
@@ -1043,8 +1063,11 @@ int csr_run(spmv_b200_csr *h, int kernel, int wpb, long long row0, long long row
       }
 
       const bool sell_kernel_id = kernel == SPMV_B200_CSR_ADAPTIVE || kernel == SPMV_B200_CSR_STREAM;
-      if (sell_kernel_id && whole && epi_mode != EPI_PUSH && csr_wants_sell(h) &&
-          csr_ensure_sell(h) == 0) {
+      // (the push epilogue exists for the panel form without long-row kernels: the shards of a
+      // general matrix whose next x slice every peer needs)
+      if (sell_kernel_id && whole && csr_wants_sell(h) &&
+          (epi_mode != EPI_PUSH || (h->segs[0].regular && g_knobs.sell != 1)) && csr_ensure_sell(h) == 0 &&
+          (epi_mode != EPI_PUSH || (h->sell.chunk == 0 && h->sell.n_long == 0))) {
             const SellPlan &sp = h->sell;
             if (epi_mode == EPI_FUSED) {
                   if (sp.K > 1 || sp.n_long || sp.n_split_rows)
@@ -1104,6 +1127,30 @@ int csr_run(spmv_b200_csr *h, int kernel, int wpb, long long row0, long long row
       if (e != cudaSuccess)
             return fail(-EIO, "CSR kernel %d launch failed: %s", kernel, cudaGetErrorString(e));
       return 0;
+}
+
+// y = A x over the whole matrix, plain epilogue, with `done(r0, r1)` called as soon as rows
+// [r0, r1) of y are final in stream order: in up to `blocks` pieces where the route allows it (the
+// column-panel form of SELL-P: the last panel runs window range by window range), once at the end
+// otherwise.  The multi-GPU all-gather hands finished pieces to the copy engines while the rest
+// of the step still computes.
+int csr_run_blocks(spmv_b200_csr *h, int kernel, int wpb, const double *d_x, double *d_y, void *stream,
+                   int blocks, const std::function<void(long long, long long)> &done) {
+      if (!h)
+            return fail(-EINVAL, "null CSR handle");
+      const bool sell_kernel_id = kernel == SPMV_B200_CSR_ADAPTIVE || kernel == SPMV_B200_CSR_STREAM;
+      if (blocks > 1 && sell_kernel_id && csr_wants_sell(h) && csr_ensure_sell(h) == 0 &&
+          h->sell.chunk == 0 && h->sell.n_long == 0) {
+            int rc = sell_run(h->sell, clamp_wpb(wpb), d_x, d_y, EPI_PLAIN, EpiArgs{}, as_stream(stream), blocks, &done);
+            cudaError_t e = cudaGetLastError();
+            if (!rc && e != cudaSuccess)
+                  rc = fail(-EIO, "SELL-P launch failed: %s", cudaGetErrorString(e));
+            return rc;
+      }
+      int rc = csr_run(h, kernel, wpb, 0, h->M, d_x, d_y, EPI_PLAIN, EpiArgs{}, stream);
+      if (!rc)
+            done(0, h->M);
+      return rc;
 }
 
 // Largest column referenced by entries [k0, k1): a device reduction (the host-buffer pipeline
@@ -1486,8 +1533,8 @@ extern "C" int spmv_b200_csr_spmv_rows_push(spmv_b200_csr *h, int kernel, int wp
                                             int n_push, const int64_t *push_row0,
                                             const int64_t *push_row1, double *const *d_push_dst,
                                             void *stream) {
-      if (n_push < 0 || n_push > 2)
-            return fail(-EINVAL, "n_push must be 0..2");
+      if (n_push < 0 || n_push > kMaxPush)
+            return fail(-EINVAL, "n_push must be 0..%d", kMaxPush);
       EpiArgs p{};
       p.n_push = n_push;
       for (int i = 0; i < n_push; ++i) {

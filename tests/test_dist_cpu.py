@@ -85,14 +85,26 @@ def test_exchange_plan_shapes():
     q = D.Plan(0, full)
     assert q.segments == [(0, 50, True)] and q.cuts == []
     assert q.mode == "push" and q.all_gather    # one peer: the push epilogue can feed it
-    # ... on 4 ranks one segment would have to feed 3 peers: the fused epilogue (2 targets)
-    # cannot, every rank agrees on the NCCL exchange; asking for PUSH is an error
+    # ... on 4 ranks one segment feeds 3 peers: still the fused epilogue (up to 8 targets: the
+    # all-gather of a general matrix is peer stores from the SpMV kernel), unless
+    # SPMV_B200_PUSH_ALL=0 asks for the NCCL exchange; every rank agrees
     full4 = [(25 * r, 25 * r + 25, 0, 100) for r in range(4)]
     for r in range(4):
         p = D.Plan(r, full4)
-        assert p.mode == "nccl" and p.all_gather
+        assert p.mode == "push" and p.all_gather and len(p.send) == 3
+    os.environ["SPMV_B200_PUSH_ALL"] = "0"
+    try:
+        for r in range(4):
+            assert D.Plan(r, full4).mode == "nccl"
+        assert D.Plan(1, full4, mode="push").mode == "push"      # asked for explicitly
+        assert D.Plan(0, full).mode == "push"                    # halo-sized plans are not affected
+    finally:
+        del os.environ["SPMV_B200_PUSH_ALL"]
+    # ten ranks: nine targets per segment are more than one launch can feed
+    full10 = [(10 * r, 10 * r + 10, 0, 100) for r in range(10)]
+    assert D.Plan(3, full10).mode == "nccl"
     with pytest.raises(RuntimeError):
-        D.Plan(1, full4, mode="push")
+        D.Plan(3, full10, mode="push")
     # unequal slices: all ranks need everything but ncclAllGather cannot be used
     ragged = [(0, 30, 0, 100), (30, 100, 0, 100)]
     assert not D.Plan(0, ragged).all_gather

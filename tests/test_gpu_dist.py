@@ -168,16 +168,23 @@ def test_single_process_group(sp, O, kind):
     sp.release_all()
 
 
-@pytest.mark.parametrize("spec,mode", [("stencil:48:40:64", "auto"), ("upper:60000:200", "push"),
-                                       ("uniform:200000:16", "auto"), ("stencil:32:32:40", "nccl")])
-def test_dist_check_binary(spec, mode):
+@pytest.mark.parametrize("spec,mode,knobs", [
+    ("stencil:48:40:64", "auto", ()), ("upper:60000:200", "push", ()), ("uniform:200000:16", "auto", ()),
+    ("stencil:32:32:40", "nccl", ()), ("uniform:200000:16", "nccl", ()),
+    # general matrix through column panels: the last panel's epilogue adds, stores and pushes the
+    # finished sums to every peer (the all-gather fused into the SpMV: EPI_ACC_PUSH)
+    ("uniform:200000:16", "push", ("sell_panels=2",)), ("uniform:300000:24", "auto", ("sell_panels=3",)),
+    # power-law rows: every peer needs every slice, the binned kernels push
+    ("rmat:16:8", "auto", ()), ("rmat:16:8", "nccl", ())])
+def test_dist_check_binary(spec, mode, knobs):
     """The C program: N GPUs vs one GPU through the C ABI only."""
     import torch
     n = min(torch.cuda.device_count(), 4)
     if n < 2:
         pytest.skip("needs 2 GPUs")
     exe = os.path.join(ROOT, "bin", "dist_check")
-    r = subprocess.run([exe, "--gpus", str(n), "--steps", "6", "--matrix", spec, "--mode", mode],
+    extra = [a for k in knobs for a in ("--knob", k)]
+    r = subprocess.run([exe, "--gpus", str(n), "--steps", "6", "--matrix", spec, "--mode", mode] + extra,
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "PASS" in r.stdout

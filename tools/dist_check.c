@@ -1,8 +1,9 @@
 /* dist_check.c -- multi-GPU iterated SpMV through the C ABI only (no Python in the loop).
  *
- *   dist_check [--gpus N] [--steps K] [--mode auto|push|nccl] [--matrix SPEC] [--bench]
+ *   dist_check [--gpus N] [--steps K] [--mode auto|push|nccl] [--matrix SPEC] [--bench] [--knob key=value]
  *   SPEC: stencil:NX:NY:NZ (generated per shard in HBM) | c5 (= stencil:512:512:512) |
- *         upper:N:W (upper-banded, structurally NON-symmetric) | uniform:N:K | poisson:NX:NY
+ *         upper:N:W (upper-banded, structurally NON-symmetric) | uniform:N:K | poisson:NX:NY |
+ *         rmat:SCALE:EDGEFACTOR (power-law rows and columns)
  *
  * One process drives N GPUs (spmv_b200_dist_group_*).  x_K = A^K x_0 from the N-GPU run is
  * compared with the same K steps on ONE GPU (resident handle, device buffers): identical kernels
@@ -62,6 +63,14 @@ int main(int argc, char **argv) {
                   spec = argv[++i];
             else if (!strcmp(argv[i], "--bench"))
                   bench = 1;
+            else if (!strcmp(argv[i], "--knob") && i + 1 < argc) { /* key=value, see spmv_b200_set_knob */
+                  char key[64];
+                  int val = 0;
+                  if (sscanf(argv[++i], "%63[^=]=%d", key, &val) != 2 || spmv_b200_set_knob(key, val)) {
+                        fprintf(stderr, "dist_check: bad --knob %s\n", argv[i]);
+                        return 2;
+                  }
+            }
             else if (!strcmp(argv[i], "--mode") && i + 1 < argc) {
                   const char *m = argv[++i];
                   mode = !strcmp(m, "push") ? SPMV_B200_DIST_PUSH
@@ -92,6 +101,15 @@ int main(int argc, char **argv) {
                   A = gen_uniform_random(a, b, 42);
             else if (sscanf(spec, "poisson:%d:%d", &a, &b) == 2)
                   A = gen_poisson2d(a, b);
+            else if (sscanf(spec, "rmat:%d:%d", &a, &b) == 2) {
+                  A = gen_rmat(a, b, 0.57, 0.19, 0.19, 42);
+                  int longest = 1; /* keep |x_k| bounded: row sums of |a| below 1 */
+                  for (int r = 0; A && r < A->M; ++r)
+                        if (A->IRP[r + 1] - A->IRP[r] > longest)
+                              longest = A->IRP[r + 1] - A->IRP[r];
+                  for (int k = 0; A && k < A->NZ; ++k)
+                        A->AS[k] /= longest;
+            }
             if (!A) {
                   fprintf(stderr, "dist_check: cannot build matrix '%s'\n", spec);
                   return 2;
