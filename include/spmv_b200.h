@@ -139,7 +139,7 @@ int spmv_b200_csr_spmv_rows(spmv_b200_csr *h, int kernel, int warps_per_block,
                             double *d_y, void *stream);
 /* Fused epilogue for the multi-GPU halo exchange: besides y[row], rows in
  * [push_row0[i], push_row1[i]) are also stored to d_push_dst[i][row -
- * push_row0[i]] (a peer GPU's halo buffer mapped through CUDA IPC).  Up to 2
+ * push_row0[i]] (a peer GPU's halo buffer mapped through CUDA IPC).  Up to 8
  * push ranges. */
 int spmv_b200_csr_spmv_rows_push(spmv_b200_csr *h, int kernel,
                                  int warps_per_block, int64_t row0,
@@ -278,8 +278,11 @@ int spmv_b200_wait_peers(const void *d_epoch, int n, void *const *d_my_slots,
 #define SPMV_B200_MAX_RANKS 16
 #define SPMV_B200_DIST_BLOB_BYTES 512
 enum spmv_b200_dist_mode {
-      SPMV_B200_DIST_AUTO = 0, /* PUSH when the plan allows it, else NCCL */
-      SPMV_B200_DIST_PUSH = 1, /* halo pushed by the SpMV epilogue into peer HBM, epoch flags */
+      SPMV_B200_DIST_AUTO = 0, /* PUSH when the plan allows it (at most 8 peers per boundary segment and
+                                  SPMV_B200_PUSH_ALL != 0 for more than 2), else NCCL */
+      SPMV_B200_DIST_PUSH = 1, /* peer HBM written directly, epoch flags: halo rows by the SpMV epilogue;
+                                  whole slices of a general matrix as row-block peer copies behind the
+                                  running step (SPMV_B200_GATHER_BLOCKS, default 2) */
       SPMV_B200_DIST_NCCL = 2  /* ncclAllGather / grouped ncclSend+ncclRecv on a side stream */
 };
 
