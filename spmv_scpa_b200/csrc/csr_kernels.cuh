@@ -547,18 +547,50 @@ __global__ void __launch_bounds__(THREADS + (WS ? 32 : 0))
 // buffers, every lane then walks its own row in shared memory (row starts are ~5 words apart:
 // conflict-free), and the row offsets of the group after next are loaded while the current one is
 // computed.  No CTA-wide synchronisation, no plan arrays.  The launcher guarantees rows <= 8.
-template <int STAGES, typename OffT>
+// One group of the pipelined short-row kernel: W (compile time, 1..8) entries per lane at most.
+template <int W>
+__device__ __forceinline__ double csr_pipe_rows(const double *__restrict__ tas, const int *__restrict__ tja,
+                                                int k0, int len, const double *__restrict__ x,
+                                                uint64_t pol_x) {
+      double a[W], xv[W];
+      int c[W];
+#pragma unroll
+      for (int u = 0; u < W; ++u) {
+            const bool ok = u < len;
+            c[u] = ok ? tja[k0 + u] : -1;
+            a[u] = ok ? tas[k0 + u] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < W; ++u)
+            xv[u] = c[u] >= 0 ? ld_x(x + c[u], pol_x) : 0.0;
+      double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+      for (int u = 0; u < W; ++u) { // even entries into acc0, odd ones into acc1: the order of every other kernel
+            if (u & 1)
+                  acc1 = fma(a[u], xv[u], acc1);
+            else
+                  acc0 = fma(a[u], xv[u], acc0);
+      }
+      return acc0 + acc1;
+}
+
+template <int STAGES, int CAPW, typename OffT>
 __global__ void __launch_bounds__(256)
     csr_pipe_kernel(const OffT *__restrict__ irp, const int *__restrict__ ja,
-                    const double *__restrict__ as, long long row0, long long row1, int capw,
+                    const double *__restrict__ as, long long row0, int n_rows,
                     const double *__restrict__ x, double *__restrict__ y) {
       extern __shared__ __align__(128) unsigned char smem_raw[];
+      constexpr int kStageBytes = CAPW * 12;
       const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
-      unsigned char *ring = smem_raw + (size_t)warp * STAGES * capw * 12;
-      uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)wpc * STAGES * capw * 12) + warp * STAGES;
-      const long long W = (long long)gridDim.x * wpc;
-      const long long first = (long long)blockIdx.x * wpc + warp;
-      const long long n_groups = (row1 - row0 + 31) >> 5;
+      unsigned char *ring = smem_raw + warp * (STAGES * kStageBytes);
+      uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + wpc * (STAGES * kStageBytes)) + warp * STAGES;
+      // groups of 32 rows, dealt round-robin to the warps of the grid; 32-bit arithmetic throughout
+      // (a shard has fewer than 2^31 rows), the row offsets themselves are OffT
+      const int W = (int)gridDim.x * wpc;
+      const int first = (int)blockIdx.x * wpc + warp;
+      const int n_groups = (n_rows + 31) >> 5;
+      irp += row0;
+      y += row0;
       const uint64_t pol_s = policy_evict_first();
       const uint64_t pol_x = policy_evict_last();
       if (lane == 0) {
@@ -570,84 +602,73 @@ __global__ void __launch_bounds__(256)
       __syncwarp();
 
       // row offsets of group g: this lane's row [lo, hi), the group's entries [k_lo, k_hi)
-      auto offsets = [&](long long g, long long &lo, long long &hi, long long &k_lo, long long &k_hi) {
-            const long long r = row0 + (g << 5) + lane;
-            lo = (long long)irp[min(r, row1)];
-            k_hi = (long long)irp[min(row0 + ((g + 1) << 5), row1)];
+      auto offsets = [&](int g, OffT &lo, OffT &hi, OffT &k_lo, OffT &k_hi) {
+            lo = irp[min(g * 32 + lane, n_rows)];
+            k_hi = irp[min(g * 32 + 32, n_rows)];
             hi = __shfl_down_sync(0xffffffffu, lo, 1);
             if (lane == 31)
                   hi = k_hi;
             k_lo = __shfl_sync(0xffffffffu, lo, 0);
       };
-      int s0[STAGES] = {0}, s1[STAGES] = {0}; // this lane's entries inside the stage's buffer
-      auto fetch = [&](int s, long long lo, long long hi, long long k_lo, long long k_hi) {
+      int s0[STAGES] = {0}, len[STAGES] = {0}; // this lane's entries inside the stage's buffer
+      auto fetch = [&](int s, OffT lo, OffT hi, OffT k_lo, OffT k_hi) {
             // (rounding out to 128-byte lines instead measured the same: profiles/r2_kbench_poisson3000_pipe.txt)
-            const long long ka = k_lo & ~3ll, kb = (k_hi + 3) & ~3ll;
-            s0[s] = (int)(lo - ka), s1[s] = (int)(hi - ka);
+            const OffT ka = k_lo & ~(OffT)3, kb = (k_hi + 3) & ~(OffT)3;
+            s0[s] = (int)(lo - ka), len[s] = (int)(hi - lo);
             if (lane == 0) {
-                  const long long cnt = kb - ka;
-                  mbar_expect_tx(&bars[s], (uint32_t)(cnt * 12));
+                  const uint32_t cnt = (uint32_t)(kb - ka);
+                  mbar_expect_tx(&bars[s], cnt * 12);
                   if (cnt > 0) {
-                        bulk_g2s(ring + (size_t)s * capw * 12, as + ka, (uint32_t)(cnt * 8), &bars[s], pol_s);
-                        bulk_g2s(ring + (size_t)s * capw * 12 + (size_t)capw * 8, ja + ka, (uint32_t)(cnt * 4),
-                                 &bars[s], pol_s);
+                        bulk_g2s(ring + s * kStageBytes, as + ka, cnt * 8, &bars[s], pol_s);
+                        bulk_g2s(ring + s * kStageBytes + CAPW * 8, ja + ka, cnt * 4, &bars[s], pol_s);
                   }
             }
       };
 #pragma unroll
       for (int s = 0; s < STAGES; ++s) {
-            const long long g = first + s * W;
-            s0[s] = s1[s] = 0;
+            const int g = first + s * W;
             if (g < n_groups) {
-                  long long lo, hi, k_lo, k_hi;
+                  OffT lo, hi, k_lo, k_hi;
                   offsets(g, lo, hi, k_lo, k_hi);
                   fetch(s, lo, hi, k_lo, k_hi);
             }
       }
-      for (long long i = 0;; i += STAGES) {
-            const uint32_t parity = (uint32_t)(i / STAGES) & 1u;
+      uint32_t parity = 0;
+      for (int g0 = first;; g0 += STAGES * W, parity ^= 1u) {
 #pragma unroll
             for (int s = 0; s < STAGES; ++s) {
-                  const long long g = first + (i + s) * W;
+                  const int g = g0 + s * W;
                   if (g >= n_groups)
                         return; // whole warp
-                  const long long gn = g + STAGES * W;
-                  long long lo = 0, hi = 0, k_lo = 0, k_hi = 0;
+                  const int gn = g + STAGES * W;
+                  OffT lo = 0, hi = 0, k_lo = 0, k_hi = 0;
                   if (gn < n_groups)
                         offsets(gn, lo, hi, k_lo, k_hi); // on their way while this group is computed
                   mbar_wait(&bars[s], parity);
-                  const double *tas = reinterpret_cast<const double *>(ring + (size_t)s * capw * 12);
-                  const int *tja = reinterpret_cast<const int *>(ring + (size_t)s * capw * 12 + (size_t)capw * 8);
-                  const int k0 = s0[s], len = s1[s] - k0;
-                  const int wmax = __reduce_max_sync(0xffffffffu, len);
-                  constexpr int U = 8;
-                  double acc0 = 0.0, acc1 = 0.0;
-                  for (int j = 0; j < wmax; j += U) {
-                        double a[U], xv[U];
-                        int c[U];
-                        bool okm[U];
-#pragma unroll
-                        for (int u = 0; u < U; ++u) {
-                              const bool ok = j + u < len;
-                              okm[u] = ok;
-                              c[u] = ok ? tja[k0 + j + u] : 0;
-                              a[u] = ok ? tas[k0 + j + u] : 0.0;
-                        }
-#pragma unroll
-                        for (int u = 0; u < U; ++u)
-                              xv[u] = okm[u] ? ld_x(x + c[u], pol_x) : 0.0;
-#pragma unroll
-                        for (int u = 0; u < U; u += 2) {
-                              acc0 = fma(a[u], xv[u], acc0);
-                              acc1 = fma(a[u + 1], xv[u + 1], acc1);
-                        }
+                  const double *tas = reinterpret_cast<const double *>(ring + s * kStageBytes);
+                  const int *tja = reinterpret_cast<const int *>(ring + s * kStageBytes + CAPW * 8);
+                  const int k0 = s0[s], n = len[s];
+                  // exactly as many entry slots as the longest row of the group needs (<= 8 by the
+                  // launcher's guarantee): a 5-point row costs 5 gathers, not 8 predicated ones
+                  const int wmax = __reduce_max_sync(0xffffffffu, n);
+                  double acc;
+                  switch (wmax) {
+                  case 0: acc = 0.0; break;
+                  case 1: acc = csr_pipe_rows<1>(tas, tja, k0, n, x, pol_x); break;
+                  case 2: acc = csr_pipe_rows<2>(tas, tja, k0, n, x, pol_x); break;
+                  case 3: acc = csr_pipe_rows<3>(tas, tja, k0, n, x, pol_x); break;
+                  case 4: acc = csr_pipe_rows<4>(tas, tja, k0, n, x, pol_x); break;
+                  case 5: acc = csr_pipe_rows<5>(tas, tja, k0, n, x, pol_x); break;
+                  case 6: acc = csr_pipe_rows<6>(tas, tja, k0, n, x, pol_x); break;
+                  case 7: acc = csr_pipe_rows<7>(tas, tja, k0, n, x, pol_x); break;
+                  default: acc = csr_pipe_rows<8>(tas, tja, k0, n, x, pol_x); break;
                   }
                   __syncwarp(); // every lane has read the stage: it may be overwritten
                   if (gn < n_groups)
                         fetch(s, lo, hi, k_lo, k_hi);
-                  const long long r = row0 + (g << 5) + lane;
-                  if (r < row1)
-                        y[r] = acc0 + acc1;
+                  const int r = g * 32 + lane;
+                  if (r < n_rows)
+                        y[r] = acc;
             }
       }
 }

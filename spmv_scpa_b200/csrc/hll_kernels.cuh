@@ -275,6 +275,31 @@ __global__ void __launch_bounds__(WARPS * 32)
 // after those are already in registers, and the only latency left on the critical path of a hack
 // is its gather of x.  Hacks are dealt round-robin (warp w: w, w + W, ...), so neighbouring warps
 // stream neighbouring memory.
+// One hack of exactly W slot columns out of a shared-memory stage, lane = row.
+template <int W>
+__device__ __forceinline__ double hll_pipe_cols(const double *__restrict__ tas, const int *__restrict__ tja,
+                                                int lane, const double *__restrict__ x, uint64_t pol_x) {
+      double a[W], xv[W];
+      int c[W];
+#pragma unroll
+      for (int u = 0; u < W; ++u) {
+            c[u] = tja[u * 32 + lane];
+            a[u] = tas[u * 32 + lane];
+      }
+#pragma unroll
+      for (int u = 0; u < W; ++u)
+            xv[u] = ld_x(x + c[u], pol_x);
+      double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+      for (int u = 0; u < W; ++u) { // even slot columns into acc0, odd into acc1, like hll_warp_kernel
+            if (u & 1)
+                  acc1 = fma(a[u], xv[u], acc1);
+            else
+                  acc0 = fma(a[u], xv[u], acc0);
+      }
+      return acc0 + acc1;
+}
+
 template <int STAGES, int EPI>
 __global__ void __launch_bounds__(256)
     hll_pipe_kernel(const long long *__restrict__ hoff, const int *__restrict__ ja,
@@ -333,27 +358,18 @@ __global__ void __launch_bounds__(256)
                   mbar_wait(&bars[s], parity);
                   const double *tas = reinterpret_cast<const double *>(ring + (size_t)s * capw * 12);
                   const int *tja = reinterpret_cast<const int *>(ring + (size_t)s * capw * 12 + (size_t)capw * 8);
-                  constexpr int U = 8;
-                  double acc0 = 0.0, acc1 = 0.0;
-                  for (int j = 0; j < width; j += U) {
-                        double a[U], xv[U];
-                        int c[U];
-                        bool okm[U];
-#pragma unroll
-                        for (int u = 0; u < U; ++u) {
-                              const bool ok = j + u < width;
-                              okm[u] = ok;
-                              c[u] = ok ? tja[(j + u) * 32 + lane] : 0;
-                              a[u] = ok ? tas[(j + u) * 32 + lane] : 0.0;
-                        }
-#pragma unroll
-                        for (int u = 0; u < U; ++u)
-                              xv[u] = okm[u] ? ld_x(x + c[u], pol_x) : 0.0;
-#pragma unroll
-                        for (int u = 0; u < U; u += 2) {
-                              acc0 = fma(a[u], xv[u], acc0);
-                              acc1 = fma(a[u + 1], xv[u + 1], acc1);
-                        }
+                  // exactly `width` slot columns (<= 8 by the launcher's choice): no predicated spares
+                  double acc;
+                  switch (width) {
+                  case 0: acc = 0.0; break;
+                  case 1: acc = hll_pipe_cols<1>(tas, tja, lane, x, pol_x); break;
+                  case 2: acc = hll_pipe_cols<2>(tas, tja, lane, x, pol_x); break;
+                  case 3: acc = hll_pipe_cols<3>(tas, tja, lane, x, pol_x); break;
+                  case 4: acc = hll_pipe_cols<4>(tas, tja, lane, x, pol_x); break;
+                  case 5: acc = hll_pipe_cols<5>(tas, tja, lane, x, pol_x); break;
+                  case 6: acc = hll_pipe_cols<6>(tas, tja, lane, x, pol_x); break;
+                  case 7: acc = hll_pipe_cols<7>(tas, tja, lane, x, pol_x); break;
+                  default: acc = hll_pipe_cols<8>(tas, tja, lane, x, pol_x); break;
                   }
                   __syncwarp(); // every lane has read the stage: it may be overwritten
                   b0[s] = n0, b1[s] = n1;
@@ -362,7 +378,7 @@ __global__ void __launch_bounds__(256)
                   double dot_acc = 0.0;
                   const long long r = h * kHack + lane;
                   if (r < M)
-                        store_y<EPI>(y, r, acc0 + acc1, epi, dot_acc);
+                        store_y<EPI>(y, r, acc, epi, dot_acc);
                   epi_finish_warp<EPI>(epi, dot_acc, h - hack0);
             }
       }

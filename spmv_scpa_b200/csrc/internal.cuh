@@ -125,6 +125,7 @@ struct Segment {
       RowList lists[kNumKinds];
       SplitPlan split;
       long long kind_rows[kNumKinds] = {0};
+      long long max_len = 0; // longest row of the segment
       // stream plans, one per kernel configuration
       std::map<int, StreamPlan> stream;
 };

@@ -140,8 +140,12 @@ static int build_split(const spmv_b200_csr *h, const std::vector<int> &rows, Spl
 int build_adaptive(spmv_b200_csr *h, Segment &sg) {
       const long long rows = sg.r1 - sg.r0;
       std::fill(sg.kind_rows, sg.kind_rows + kNumKinds, 0);
-      for (long long r = sg.r0; r < sg.r1; ++r)
-            ++sg.kind_rows[kind_of(h->h_irp[r + 1] - h->h_irp[r])];
+      sg.max_len = 0;
+      for (long long r = sg.r0; r < sg.r1; ++r) {
+            const long long len = h->h_irp[r + 1] - h->h_irp[r];
+            ++sg.kind_rows[kind_of(len)];
+            sg.max_len = std::max(sg.max_len, len);
+      }
 
       // "regular" matrix: one bin holds the bulk of the rows and nearly all
       // other rows are shorter -> run ONE launch over the contiguous range
@@ -945,21 +949,15 @@ int csr_ensure_sell(spmv_b200_csr *h) {
 // ================================================================== routing
 namespace b200 {
 
-static bool segment_max_row_at_most_8(const Segment &sg) {
-      static_assert(kKindMax[1] == kCsrPipeMaxRow, "bins 0 and 1 hold the rows of at most 8 entries");
-      for (int k = 2; k < kNumKinds; ++k)
-            if (sg.kind_rows[k])
-                  return false;
-      return sg.r1 > sg.r0;
-}
-
-// 0 launched, < 0 error
-template <typename OffT>
-static int launch_csr_pipe(const CsrArgs &a, long long r0, long long r1) {
+// 0 launched, < 0 error.  CAPW = entries a warp's buffer holds: 32 rows of at most MAXROW entries,
+// rounded out to multiples of 4 at both ends.  Two sizes: rows <= 5 (5-point stencils: 4.2 KB per
+// warp, 48 warps per SM) and rows <= 8 (6.5 KB, 32 warps).
+template <typename OffT, int MAXROW>
+static int launch_csr_pipe_cap(const CsrArgs &a, long long r0, long long r1) {
       constexpr int kStages = 2, kWarps = 8;
-      constexpr int capw = 32 * kCsrPipeMaxRow + 16; // a group's entries rounded out to multiples of 4
+      constexpr int capw = 32 * MAXROW + 16;
       constexpr size_t smem = (size_t)kWarps * kStages * capw * 12 + (size_t)kWarps * kStages * 8;
-      auto kern = csr_pipe_kernel<kStages, OffT>;
+      auto kern = csr_pipe_kernel<kStages, capw, OffT>;
       static int occ_by_dev[kMaxDevices] = {0};
       int &occ = occ_by_dev[a.h->device % kMaxDevices];
       if (!occ) {
@@ -968,11 +966,18 @@ static int launch_csr_pipe(const CsrArgs &a, long long r0, long long r1) {
             if (occ < 1)
                   return fail(-EINVAL, "csr_pipe_kernel does not fit on an SM");
       }
+      if (r1 - r0 >= (1ll << 31) - 64)
+            return fail(-EINVAL, "csr_pipe_kernel: more than 2^31 rows in one segment");
       const long long groups = (r1 - r0 + 31) / 32;
       const int g = (int)std::min<long long>((groups + kWarps - 1) / kWarps, (long long)occ * g_sm_count);
-      kern<<<g, kWarps * 32, smem, a.st>>>((const OffT *)a.h->d_irp, a.h->d_ja, a.h->d_as, r0, r1, capw, a.x, a.y);
+      kern<<<g, kWarps * 32, smem, a.st>>>((const OffT *)a.h->d_irp, a.h->d_ja, a.h->d_as, r0, (int)(r1 - r0), a.x, a.y);
       ++g_counters.launches;
       return 0;
+}
+template <typename OffT>
+static int launch_csr_pipe(const CsrArgs &a, const Segment &sg) {
+      return sg.max_len <= 5 ? launch_csr_pipe_cap<OffT, 5>(a, sg.r0, sg.r1)
+                             : launch_csr_pipe_cap<OffT, kCsrPipeMaxRow>(a, sg.r0, sg.r1);
 }
 
 constexpr long long kStreamDotSlots = 32768; // >= CTAs * consumer warps of any stream launch
@@ -1009,9 +1014,9 @@ static int run_kernel(spmv_b200_csr *h, int kernel, int wpb, Segment &sg, const 
       case SPMV_B200_CSR_STREAM: {
             // short regular rows: persistent warps with private bulk-copy rings (csr_pipe_kernel)
             if (a.epi_mode == EPI_PLAIN && g_knobs.csr_pipe != 0 && g_knobs.csr_stream_cfg < 0 &&
-                segment_max_row_at_most_8(sg) &&
+                sg.r1 > sg.r0 && sg.max_len <= kCsrPipeMaxRow &&
                 (g_knobs.csr_pipe > 0 || (sg.regular && sg.r1 - sg.r0 >= 32ll * 4 * g_sm_count * 8))) {
-                  return launch_csr_pipe<OffT>(a, sg.r0, sg.r1);
+                  return launch_csr_pipe<OffT>(a, sg);
             }
             const double mean_len = sg.r1 > sg.r0 ? (double)(h->h_irp[sg.r1] - h->h_irp[sg.r0]) /
                                                         (double)(sg.r1 - sg.r0)
@@ -1781,20 +1786,20 @@ int hll_run_range(spmv_b200_hll *h, int kernel, int wpb, long long hack0, long l
             if (vec <= 1 && g_knobs.hll_pipe != 0 && h->max_width > 0 && h->max_width <= kHllPipeMaxWidth &&
                 (g_knobs.hll_pipe > 0 || n >= 4ll * g_sm_count * 8)) {
                   constexpr int kStages = 2, kWarps = 8;
-                  const int capw = 32 * kHllPipeMaxWidth;
+                  const int capw = 32 * h->max_width; // 3.8 KB per warp for width 5: 48 warps per SM
                   const size_t smem = (size_t)kWarps * kStages * capw * 12 + (size_t)kWarps * kStages * 8;
                   const int fu = epi_mode == EPI_FUSED;
-                  static int occ_by_dev[2][kMaxDevices] = {{0}};
-                  int &occ = occ_by_dev[fu][h->device % kMaxDevices];
+                  static int occ_by_dev[2][kHllPipeMaxWidth + 1][kMaxDevices] = {{{0}}};
+                  int &occ = occ_by_dev[fu][h->max_width][h->device % kMaxDevices];
                   if (!occ) {
                         if (fu) {
                               B200_CUDA(cudaFuncSetAttribute(hll_pipe_kernel<kStages, EPI_FUSED>,
-                                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 100 << 10));
                               B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
                                   &occ, hll_pipe_kernel<kStages, EPI_FUSED>, kWarps * 32, smem));
                         } else {
                               B200_CUDA(cudaFuncSetAttribute(hll_pipe_kernel<kStages, EPI_PLAIN>,
-                                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 100 << 10));
                               B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
                                   &occ, hll_pipe_kernel<kStages, EPI_PLAIN>, kWarps * 32, smem));
                         }
