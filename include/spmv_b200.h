@@ -248,9 +248,10 @@ void spmv_b200_counters(int64_t *launches, int64_t *h2d_bytes,
 
 /* Experiment knobs used by bin/kbench sweeps and tests ("csr_stream_cfg", "hll_vec",
  * "hll_stream_cfg", "regular_lpr", "adaptive_direct", "force_wide", "pipeline", "pipe_chunks",
- * "sell", "sell_panels", "sell_sigma", "sell_panel_mb", "sell_max_row", "sell_unroll", "sell_chunk", "sell_hot", "cache",
- * "l2_fetch_granularity").  0 or -EINVAL.  Knobs that change planning must be set before a
- * handle is created. */
+ * "csr_pipe", "hll_pipe" (short rows / narrow hacks through per-warp bulk-copy rings: -1 auto, 0 off,
+ * 1 whenever they fit), "sell", "sell_panels", "sell_sigma", "sell_panel_mb", "sell_max_row",
+ * "sell_unroll", "sell_chunk", "sell_hot", "sell_hot_mode", "cache", "l2_fetch_granularity").
+ * 0 or -EINVAL.  Knobs that change planning must be set before a handle is created. */
 int spmv_b200_set_knob(const char *key, int value);
 
 /* ---- inter-process peer memory (one process per GPU) --------------------- */
