@@ -88,6 +88,10 @@ int spmv_b200_host_free(void *ptr);
  * before freeing it; the host-pointer calls use registered buffers in place. */
 int spmv_b200_host_register(void *ptr, size_t bytes);
 int spmv_b200_host_unregister(void *ptr);
+/* memcpy on the library's copy threads (what the host-buffer calls use between pageable memory
+ * and their page-locked bounce buffers: non-temporal stores, the CPUs the cpuset allows;
+ * SPMV_B200_COPY_THREADS overrides the team size). */
+int spmv_b200_host_copy(void *dst, const void *src, size_t bytes);
 /* Overwrite a scratch buffer four times the size of the L2, then read half of it back, so the
  * next launch starts cold AND the L2 holds no dirty lines whose write-back it would pay for. */
 int spmv_b200_flush_l2(void *stream);
