@@ -151,6 +151,12 @@ int spmv_b200_csr_spmv_rows_push(spmv_b200_csr *h, int kernel,
                                  int n_push, const int64_t *push_row0,
                                  const int64_t *push_row1,
                                  double *const *d_push_dst, void *stream);
+/* K right-hand sides in one pass: Y = A X with X[n_local][k] and Y[M][k] row-major
+ * (the k values of a row are adjacent), k = 2 or 4, d_X 16-byte aligned.  Same routes as kernel id 2
+ * (sorted slices for ragged rows / scattered columns, rows straight from CSR otherwise); every
+ * gather returns k useful values from the 32-byte sector it moves, so gather-bound matrices
+ * (BASELINE configs[2], [3]) run close to k times the single-vector rate.  Asynchronous on `stream`. */
+int spmv_b200_csr_spmm(spmv_b200_csr *h, int k, const double *d_X, double *d_Y, void *stream);
 /* Fused iteration step (the loop around reference src/csr.c:182-199 when SpMV is
  * iterated): y = alpha * A x + beta * z in one pass over the matrix, and, when d_dot is
  * non-NULL, *d_dot = sum_i y_i * w_i (d_w may be d_y for ||y||^2; d_z and d_w may be NULL).

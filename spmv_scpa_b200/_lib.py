@@ -133,6 +133,7 @@ _sig(b200, "spmv_b200_host_copy", C.c_int, vp, vp, C.c_size_t)
 _sig(b200, "spmv_b200_host_unregister", C.c_int, vp)
 _sig(b200, "spmv_b200_set_cache_policy", C.c_int, C.c_int)
 _sig(b200, "spmv_b200_invalidate", None, vp)
+_sig(b200, "spmv_b200_csr_spmm", C.c_int, vp, C.c_int, vp, vp, vp)
 _sig(b200, "spmv_b200_csr_spmv_fused", C.c_int, vp, C.c_int, C.c_int, vp, vp, C.c_double, C.c_double,
      vp, vp, vp, vp)
 _sig(b200, "spmv_b200_hll_spmv_fused", C.c_int, vp, C.c_int, C.c_int, vp, vp, C.c_double, C.c_double,

@@ -431,6 +431,15 @@ class CsrDevice:
                                                     _stream_ptr(stream)))
         return y
 
+    def spmm(self, X, Y, stream=None):
+        """Y[M, k] = A X[N, k] for k = 2 or 4 right-hand sides, both row-major CUDA tensors
+        (spmv_b200_csr_spmm): one pass over the matrix."""
+        k = int(X.shape[1])
+        assert X.is_contiguous() and Y.is_contiguous() and tuple(Y.shape) == (self.M, k) and X.shape[0] >= self.N
+        self._check(L.b200.spmv_b200_csr_spmm(self._h, k, _dev_ptr(X, self.N * k, "X"), _dev_ptr(Y, self.M * k, "Y"),
+                                              _stream_ptr(stream)))
+        return Y
+
     def spmv_host(self, x, y, kernel=4, warps_per_block=4):
         """Host x (numpy, N) in, host y (numpy, M) out: upload, kernels and download pipelined
         (spmv_b200_csr_spmv_host).  Returns the span of the kernels in ms."""

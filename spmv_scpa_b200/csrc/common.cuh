@@ -146,6 +146,20 @@ __device__ __forceinline__ double ld_x(const double *p, uint64_t pol) {
       return v;
 }
 
+// K consecutive values X[c*K .. c*K + K) of a row-major block of K right-hand sides (SpMM): one
+// or two 16-byte loads out of the SAME 32-byte sector a single-vector gather would fetch for 8
+// useful bytes.
+template <int K>
+__device__ __forceinline__ void ld_xk(const double *X, int c, uint64_t pol, double (&v)[K]) {
+      static_assert(K == 2 || K == 4, "2 or 4 right-hand sides");
+      const double *p = X + (long long)c * K;
+#pragma unroll
+      for (int j = 0; j < K; j += 2)
+            asm("ld.global.nc.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;"
+                : "=d"(v[j]), "=d"(v[j + 1])
+                : "l"(p + j), "l"(pol));
+}
+
 // --------------------------------------------------- mbarrier + bulk copy --
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
       return static_cast<uint32_t>(__cvta_generic_to_shared(p));

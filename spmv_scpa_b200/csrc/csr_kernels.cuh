@@ -540,6 +540,87 @@ __global__ void __launch_bounds__(THREADS + (WS ? 32 : 0))
 }
 
 // ------------------------------------------------------------------------
+// K right-hand sides straight from CSR (Y[M][K] = A X[N][K], row-major): LPR lanes per row, the
+// lanes of a row combined with shuffles.  The route of matrices that have no SELL-P plan (regular
+// rows with local columns) and of rows too long for a slice.
+template <int K, int LPR, typename OffT>
+__global__ void __launch_bounds__(512)
+    csr_mm_kernel(const OffT *__restrict__ irp, const int *__restrict__ ja,
+                  const double *__restrict__ as, long long row0, long long nrows,
+                  const int *__restrict__ rowlist, const double *__restrict__ X,
+                  double *__restrict__ Y) {
+      const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+      const long long g = gid / LPR;
+      const int sub = (int)(gid % LPR);
+      if (g >= nrows)
+            return; // whole groups leave together
+      const long long row = rowlist ? (long long)rowlist[g] : row0 + g;
+      const OffT s = irp[row], e = irp[row + 1];
+      const uint64_t pol_s = policy_evict_first();
+      const uint64_t pol_x = policy_evict_last();
+      constexpr int U = 4;
+      double acc[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+            acc[k] = 0.0;
+      for (OffT k0 = s + sub; k0 < e; k0 += LPR * U) {
+            double a[U], xv[U][K];
+            int c[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                  const OffT kk = k0 + u * LPR;
+                  const bool ok = kk < e;
+                  a[u] = ok ? ld_stream_f64(as + kk, pol_s) : 0.0;
+                  c[u] = ok ? ld_stream_s32(ja + kk, pol_s) : -1;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                  if (c[u] >= 0) {
+                        ld_xk<K>(X, c[u], pol_x, xv[u]);
+                  } else {
+#pragma unroll
+                        for (int k = 0; k < K; ++k)
+                              xv[u][k] = 0.0;
+                  }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                  for (int k = 0; k < K; ++k)
+                        acc[k] = fma(a[u], xv[u][k], acc[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+            acc[k] = group_sum<LPR>(acc[k]);
+      if (sub == 0) {
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+                  Y[row * K + k] = acc[k];
+      }
+}
+
+// Y[split_row[i]][0..K) = sum of the row's pieces, in piece order
+template <int K>
+__global__ void csr_combine_mm_kernel(const int *__restrict__ split_row,
+                                      const int *__restrict__ split_first, int n_split,
+                                      const double *__restrict__ partial, double *__restrict__ Y) {
+      const int i = blockIdx.x * blockDim.x + threadIdx.x;
+      if (i >= n_split)
+            return;
+      double acc[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+            acc[k] = 0.0;
+      for (int c = split_first[i]; c < split_first[i + 1]; ++c)
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+                  acc[k] += partial[(long long)c * K + k];
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+            Y[(long long)split_row[i] * K + k] = acc[k];
+}
+
+// ------------------------------------------------------------------------
 // Short regular rows (5-point stencils, BASELINE configs[0]): the CSR twin of hll_pipe_kernel.
 // Persistent warps; a warp owns groups of 32 consecutive rows (g, g + W, ...), whose entries are
 // one contiguous piece of ja / as: lane 0 fetches it (rounded out to multiples of 4 entries, the

@@ -146,6 +146,7 @@ struct SellPlan {
       long long n_rows = 0, n_split_rows = 0, n_partials = 0;
       int *d_split_row = nullptr, *d_split_first = nullptr;
       double *d_partial = nullptr;
+      double *d_partial_mm = nullptr; // 4 partial sums per piece (SpMM), allocated on first use
       // hot-column table (virtual-row form only): columns served from shared memory
       int n_hot = 0;
       int *d_hot_cols = nullptr;
@@ -174,6 +175,7 @@ struct spmv_b200_csr {
       // consecutive rows spans, median over the sample; -1 = not measured yet
       double gather_span = -1.0;
       b200::SellPlan sell;
+      b200::SellPlan sell_mm2, sell_mm4; // SpMM with 2 / 4 right-hand sides when it needs more column panels
       // host-buffer pipeline (banded matrices): row chunks with their own launch plans, and how
       // much of x each chunk needs to have arrived
       std::vector<b200::Segment> pipe_segs;

@@ -90,6 +90,69 @@ __global__ void __launch_bounds__(1024)
       epi_finish_warp<EPI>(epi, dot_acc, s);
 }
 
+// K right-hand sides at once: Y[M][K] = A X[N][K], both row-major.  The slices are
+// walked exactly as in sell_kernel; every gather now returns K useful values out of the sector it
+// moves, which is the one way past the gather bound of DESIGN.md section 3 for callers that
+// iterate on several vectors.  EPI_PLAIN stores, EPI_ACC adds (column panels after the first);
+// pieces of split rows write K partial sums each.
+template <int K, int EPI, bool VROWS>
+__global__ void __launch_bounds__(512)
+    sell_mm_kernel(const long long *__restrict__ soff, const int *__restrict__ perm,
+                   const int *__restrict__ ja, const double *__restrict__ as, long long n_slices,
+                   const double *__restrict__ X, double *__restrict__ Y, double *__restrict__ partial) {
+      static_assert(EPI == EPI_PLAIN || EPI == EPI_ACC, "SpMM epilogues");
+      const long long s = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+      if (s >= n_slices)
+            return; // whole warp
+      const int lane = threadIdx.x & 31;
+      const long long base = soff[s];
+      const int width = (int)((soff[s + 1] - base) >> 5);
+      if (EPI == EPI_ACC && width == 0)
+            return;
+      const int row = perm[s * 32 + lane];
+      const uint64_t pol_s = policy_evict_first();
+      const uint64_t pol_x = policy_evict_last();
+      const double *sas = as + base;
+      const int *sja = ja + base;
+      constexpr int U = 4;
+      double acc[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+            acc[k] = 0.0;
+      for (int j = 0; j < width; j += U) {
+            double a[U], xv[U][K];
+            int c[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                  const int kk = (j + u) * 32 + lane;
+                  const bool ok = j + u < width;
+                  a[u] = ok ? ld_stream_f64(sas + kk, pol_s) : 0.0;
+                  c[u] = ok ? ld_stream_s32(sja + kk, pol_s) : -1;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                  if (c[u] >= 0) {
+                        ld_xk<K>(X, c[u], pol_x, xv[u]);
+                  } else {
+#pragma unroll
+                        for (int k = 0; k < K; ++k)
+                              xv[u][k] = 0.0;
+                  }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                  for (int k = 0; k < K; ++k)
+                        acc[k] = fma(a[u], xv[u][k], acc[k]);
+      }
+      double *out = row >= 0 ? Y + (long long)row * K : (VROWS && row < -1 ? partial + (long long)(-2 - row) * K : nullptr);
+      if (out) {
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+                  out[k] = (EPI == EPI_ACC && row >= 0) ? out[k] + acc[k] : acc[k];
+      }
+}
+
 // Hot-column variant (ragged matrices, one panel).  Power-law matrices are as skewed in their
 // columns as in their rows: on R-MAT scale 24 the 12 288 most referenced columns (0.07 % of x)
 // take 27 % of all gathers, the top 24 576 take 34 %.  Every gather that goes to the L2 moves a

@@ -92,7 +92,7 @@ void free_sell(SellPlan &sp) {
       free_list(sp.long_warp);
       free_list(sp.long_block);
       free_split(sp.long_split);
-      cudaFree(sp.d_split_row), cudaFree(sp.d_split_first), cudaFree(sp.d_partial);
+      cudaFree(sp.d_split_row), cudaFree(sp.d_split_first), cudaFree(sp.d_partial), cudaFree(sp.d_partial_mm);
       cudaFree(sp.d_hot_cols), cudaFree(sp.d_xhot);
       sp = SellPlan();
 }
@@ -896,34 +896,35 @@ bool csr_wants_sell(spmv_b200_csr *h) {
       return sell_panels_for(h->N, h->gather_span) > 1;
 }
 
-int csr_ensure_sell(spmv_b200_csr *h) {
-      if (h->sell.state != 0)
-            return h->sell.state == 1 ? 0 : -1;
+// `rhs` right-hand sides share one pass (SpMM): the x a panel must keep in the L2 is rhs times as large
+int csr_build_sell(spmv_b200_csr *h, SellPlan &plan, int rhs) {
+      if (plan.state != 0)
+            return plan.state == 1 ? 0 : -1;
       // Ragged / power-law rows take ONE panel whatever the size of x: their columns are as
       // skewed as their rows (R-MAT: a few hot columns serve most gathers), panels measured no
       // gain there and cost a pass over y and the row order each (profiles/r2_kbench_c4_sell.txt).
       const bool ragged = !h->segs.empty() && !h->segs[0].regular;
-      const int K = ragged && g_knobs.sell_panels <= 0 ? 1 : sell_panels_for(h->N, h->gather_span);
+      const int K = ragged && g_knobs.sell_panels <= 0 ? 1 : sell_panels_for(h->N * rhs, h->gather_span);
       // virtual rows: ragged matrices, or any one-panel plan when SELL-P is forced by the knob
       if ((ragged || g_knobs.sell == 1) && K == 1 && g_knobs.sell_panels <= 0 && g_knobs.sell_chunk > 0) {
             int rc;
             if (h->wide)
                   rc = sell_build_vrows(CsrSrc<long long>{(const long long *)h->d_irp, h->d_ja, h->d_as},
-                                        h->h_irp, h->M, h->N, g_knobs.sell_chunk, h->sell);
+                                        h->h_irp, h->M, h->N, g_knobs.sell_chunk, plan);
             else
                   rc = sell_build_vrows(CsrSrc<int>{(const int *)h->d_irp, h->d_ja, h->d_as}, h->h_irp,
-                                        h->M, h->N, g_knobs.sell_chunk, h->sell);
-            return rc || h->sell.state != 1 ? -1 : 0;
+                                        h->M, h->N, g_knobs.sell_chunk, plan);
+            return rc || plan.state != 1 ? -1 : 0;
       }
       std::vector<int> long_rows;
       int rc;
       if (h->wide)
             rc = sell_build(CsrSrc<long long>{(const long long *)h->d_irp, h->d_ja, h->d_as}, h->M,
-                            h->N, K, g_knobs.sell_max_row, h->sell, &long_rows);
+                            h->N, K, g_knobs.sell_max_row, plan, &long_rows);
       else
             rc = sell_build(CsrSrc<int>{(const int *)h->d_irp, h->d_ja, h->d_as}, h->M, h->N, K,
-                            g_knobs.sell_max_row, h->sell, &long_rows);
-      if (rc || h->sell.state != 1)
+                            g_knobs.sell_max_row, plan, &long_rows);
+      if (rc || plan.state != 1)
             return -1;
       // rows too long for a slice: a warp per row up to 2048 entries, a CTA per row up to 65 536,
       // split into chunks beyond (the bins of the direct path)
@@ -932,17 +933,19 @@ int csr_ensure_sell(spmv_b200_csr *h) {
             const long long len = h->h_irp[r + 1] - h->h_irp[r];
             (len <= kKindMax[5] ? wrp : (len <= kKindMax[6] ? blk : spl)).push_back(r);
       }
-      h->sell.n_long = (long long)long_rows.size();
-      h->sell.long_warp.n = (long long)wrp.size();
-      h->sell.long_block.n = (long long)blk.size();
-      if (upload(&h->sell.long_warp.d_rows, wrp) || upload(&h->sell.long_block.d_rows, blk) ||
-          build_split(h, spl, h->sell.long_split)) {
-            free_sell(h->sell);
-            h->sell.state = -1;
+      plan.n_long = (long long)long_rows.size();
+      plan.long_warp.n = (long long)wrp.size();
+      plan.long_block.n = (long long)blk.size();
+      if (upload(&plan.long_warp.d_rows, wrp) || upload(&plan.long_block.d_rows, blk) ||
+          build_split(h, spl, plan.long_split)) {
+            free_sell(plan);
+            plan.state = -1;
             return -1;
       }
       return 0;
 }
+
+int csr_ensure_sell(spmv_b200_csr *h) { return csr_build_sell(h, h->sell, 1); }
 
 } // namespace
 
@@ -1014,7 +1017,7 @@ static int run_kernel(spmv_b200_csr *h, int kernel, int wpb, Segment &sg, const 
       case SPMV_B200_CSR_STREAM: {
             // short regular rows: persistent warps with private bulk-copy rings (csr_pipe_kernel)
             if (a.epi_mode == EPI_PLAIN && g_knobs.csr_pipe != 0 && g_knobs.csr_stream_cfg < 0 &&
-                sg.r1 > sg.r0 && sg.max_len <= kCsrPipeMaxRow &&
+                sg.r1 > sg.r0 && sg.r1 - sg.r0 < (1ll << 31) - 64 && sg.max_len <= kCsrPipeMaxRow &&
                 (g_knobs.csr_pipe > 0 || (sg.regular && sg.r1 - sg.r0 >= 32ll * 4 * g_sm_count * 8))) {
                   return launch_csr_pipe<OffT>(a, sg);
             }
@@ -1411,7 +1414,7 @@ extern "C" void spmv_b200_csr_destroy(spmv_b200_csr *h) {
             free_segment(sg);
       for (auto &sg : h->pipe_segs)
             free_segment(sg);
-      free_sell(h->sell);
+      free_sell(h->sell), free_sell(h->sell_mm2), free_sell(h->sell_mm4);
       cudaFree(h->d_dot_partial);
       cudaFree(h->d_irp);
       cudaFree(h->d_ja);
@@ -1559,6 +1562,117 @@ extern "C" int spmv_b200_csr_spmv_fused(spmv_b200_csr *h, int kernel, int wpb, c
       e.w = d_dot ? d_w : nullptr;
       e.dot_partial = d_dot; // csr_run swaps in the per-warp scratch and reduces into d_dot
       return csr_run(h, kernel, wpb, 0, h ? h->M : 0, d_x, d_y, EPI_FUSED, e, stream);
+}
+
+// ------------------------------------------------------------------- SpMM
+namespace {
+
+template <int K, typename OffT>
+void launch_mm_rows(const spmv_b200_csr *h, int lpr_log2, long long row0, long long nrows, const int *rowlist,
+                    const double *X, double *Y, cudaStream_t st) {
+      if (nrows <= 0)
+            return;
+      const OffT *irp = (const OffT *)h->d_irp;
+      constexpr int T = 256;
+#define MM_CASE(L)                                                                                 \
+      csr_mm_kernel<K, L, OffT><<<blocks_for(nrows * L, T), T, 0, st>>>(irp, h->d_ja, h->d_as, row0, nrows, \
+                                                                         rowlist, X, Y)
+      switch (lpr_log2) {
+      case 0: MM_CASE(1); break;
+      case 1: MM_CASE(2); break;
+      case 2: MM_CASE(4); break;
+      case 3: MM_CASE(8); break;
+      case 4: MM_CASE(16); break;
+      default: MM_CASE(32); break;
+      }
+#undef MM_CASE
+      ++g_counters.launches;
+}
+
+template <int K>
+int csr_spmm_k(spmv_b200_csr *h, const double *X, double *Y, cudaStream_t st) {
+      if (csr_wants_sell(h) && csr_ensure_sell(h) == 0) {
+            // column panels are sized for the x they must keep in the L2: K right-hand sides need K
+            // times as many, i.e. a plan of their own (virtual-row plans have one panel: shared)
+            SellPlan *plan = &h->sell;
+            if (h->sell.chunk == 0 && sell_panels_for(h->N * K, h->gather_span) != h->sell.K) {
+                  plan = K == 2 ? &h->sell_mm2 : &h->sell_mm4;
+                  if (csr_build_sell(h, *plan, K))
+                        return fail(-ENOMEM, "SpMM: could not build the %d-vector slice plan", K);
+            }
+            SellPlan &sp = *plan;
+            const int threads = 128;
+            const int grid = blocks_for(sp.n_slices * 32, threads);
+            if (sp.chunk > 0) { // virtual rows: one panel, pieces of split rows combined in order
+                  if (sp.n_partials && !sp.d_partial_mm &&
+                      cudaMalloc(&sp.d_partial_mm, (size_t)sp.n_partials * 4 * sizeof(double)) != cudaSuccess)
+                        return fail(-ENOMEM, "SpMM partial sums: out of device memory");
+                  sell_mm_kernel<K, EPI_PLAIN, true><<<grid, threads, 0, st>>>(
+                      sp.d_soff, sp.d_perm, sp.d_ja, sp.d_as, sp.n_slices, X, Y, sp.d_partial_mm);
+                  ++g_counters.launches;
+                  if (sp.n_split_rows) {
+                        csr_combine_mm_kernel<K><<<blocks_for(sp.n_split_rows, 128), 128, 0, st>>>(
+                            sp.d_split_row, sp.d_split_first, (int)sp.n_split_rows, sp.d_partial_mm, Y);
+                        ++g_counters.launches;
+                  }
+                  return 0;
+            }
+            if (sp.n_hot > 0)
+                  return fail(-ENOTSUP, "SpMM: not available with the hot-column table (sell_hot knob)");
+            for (int p = 0; p < sp.K; ++p) {
+                  const long long *soff = sp.d_soff + (size_t)p * (sp.n_slices + 1);
+                  const int *perm = sp.d_perm + (size_t)p * sp.n_slices * 32;
+                  if (p == 0)
+                        sell_mm_kernel<K, EPI_PLAIN, false><<<grid, threads, 0, st>>>(soff, perm, sp.d_ja, sp.d_as,
+                                                                                      sp.n_slices, X, Y, nullptr);
+                  else
+                        sell_mm_kernel<K, EPI_ACC, false><<<grid, threads, 0, st>>>(soff, perm, sp.d_ja, sp.d_as,
+                                                                                    sp.n_slices, X, Y, nullptr);
+                  ++g_counters.launches;
+            }
+            // rows too long for a slice: a warp per row
+            const RowList lists[2] = {sp.long_warp, sp.long_block};
+            for (const RowList &l : lists) {
+                  if (h->wide)
+                        launch_mm_rows<K, long long>(h, 5, 0, l.n, l.d_rows, X, Y, st);
+                  else
+                        launch_mm_rows<K, int>(h, 5, 0, l.n, l.d_rows, X, Y, st);
+            }
+            if (sp.long_split.n_rows) {
+                  if (h->wide)
+                        launch_mm_rows<K, long long>(h, 5, 0, sp.long_split.n_rows, sp.long_split.d_row, X, Y, st);
+                  else
+                        launch_mm_rows<K, int>(h, 5, 0, sp.long_split.n_rows, sp.long_split.d_row, X, Y, st);
+            }
+            return 0;
+      }
+      // no sorted slices for this matrix: lanes per row from the mean row length
+      const double mean = h->M ? (double)h->NZ / (double)h->M : 0.0;
+      const int lg = mean <= 6 ? 1 : (mean <= 12 ? 2 : (mean <= 48 ? 3 : (mean <= 96 ? 4 : 5)));
+      if (h->wide)
+            launch_mm_rows<K, long long>(h, lg, 0, h->M, nullptr, X, Y, st);
+      else
+            launch_mm_rows<K, int>(h, lg, 0, h->M, nullptr, X, Y, st);
+      return 0;
+}
+
+} // namespace
+
+extern "C" int spmv_b200_csr_spmm(spmv_b200_csr *h, int k, const double *d_X, double *d_Y, void *stream) {
+      if (!h || !d_X || !d_Y)
+            return fail(-EINVAL, "csr_spmm: null argument");
+      if (k != 2 && k != 4)
+            return fail(-EINVAL, "csr_spmm: 2 or 4 right-hand sides (got %d)", k);
+      if (((uintptr_t)d_X & 15) || ((uintptr_t)d_Y & 7))
+            return fail(-EINVAL, "csr_spmm: X must be 16-byte aligned");
+      cudaStream_t st = as_stream(stream);
+      int rc = k == 2 ? csr_spmm_k<2>(h, d_X, d_Y, st) : csr_spmm_k<4>(h, d_X, d_Y, st);
+      if (rc)
+            return rc;
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess)
+            return fail(-EIO, "SpMM launch failed: %s", cudaGetErrorString(e));
+      return 0;
 }
 
 extern "C" int spmv_b200_csr_launches(const spmv_b200_csr *h, int kernel) {

@@ -522,6 +522,71 @@ def test_csr_pipelined_short_rows(sp, O, torch):
         sp.set_knob("force_wide", 0)
 
 
+@pytest.mark.parametrize("name", ["stencil", "poisson", "rmat", "ragged", "uniform_panels", "wide"])
+def test_spmm_matches_k_spmvs(sp, O, torch, name):
+    """Y = A X for 2 and 4 right-hand sides in one pass (spmv_b200_csr_spmm): every
+    column equals the reference serial CSR product with that column, on every route -- rows straight
+    from CSR, virtual rows with split pieces, column panels with accumulation, 64-bit offsets."""
+    make = {"stencil": lambda: sp.gen_stencil27(20, 18, 16), "poisson": lambda: sp.gen_poisson2d(150, 90),
+            "rmat": lambda: sp.gen_rmat(14, 12), "ragged": lambda: sp.gen_ragged(6000, 700),
+            "uniform_panels": lambda: sp.gen_uniform_random(30000, 24), "wide": lambda: sp.gen_ragged(3000, 90)}
+    A = make[name]()
+    IRP, JA, AS = A.IRP.copy(), A.JA.copy(), A.AS.copy()
+    rng = np.random.default_rng(31)
+    try:
+        if name == "uniform_panels":
+            sp.set_knob("sell_panels", 3)
+        if name == "wide":
+            sp.set_knob("force_wide", 1)
+            h = sp.CsrDevice.from_arrays(A.M, A.N, IRP.astype(np.int64), JA, AS)
+            sp.set_knob("force_wide", 0)
+        else:
+            h = sp.CsrDevice.from_host(A)
+        for k in (2, 4):
+            Xh = rng.uniform(-1, 1, (A.N, k))
+            X = torch.from_numpy(Xh).cuda()
+            Y = torch.full((A.M, k), float("nan"), dtype=torch.float64, device="cuda")
+            h.spmm(X, Y)
+            Yh = Y.cpu().numpy()
+            for j in range(k):
+                xj = np.ascontiguousarray(Xh[:, j])
+                ok, worst = O.check_tolerance(np.ascontiguousarray(Yh[:, j]), O.csr_spmv(A.M, IRP, JA, AS, xj),
+                                              O.csr_abs_bound(A.M, IRP, JA, AS, xj), TOL)
+                assert ok, (name, k, j, worst)
+            h.spmm(X, Y)                                   # run to run identical (no atomics anywhere)
+            assert np.array_equal(Y.cpu().numpy(), Yh)
+        with pytest.raises(RuntimeError):
+            h.spmm(torch.zeros((A.N, 3), dtype=torch.float64, device="cuda"),
+                   torch.zeros((A.M, 3), dtype=torch.float64, device="cuda"))
+        h.close()
+    finally:
+        sp.set_knob("sell_panels", 0)
+        sp.set_knob("force_wide", 0)
+
+
+def test_spmm_builds_its_own_panels_when_x_outgrows_the_l2(sp, O, torch):
+    """Column panels are sized for the x they keep in the L2; k right-hand sides make x k times as
+    large, so SpMM on a scattered matrix with a large x runs on a slice plan of its own (more
+    panels, accumulation across them) -- the C3 case at a tenth of its size."""
+    A = sp.gen_uniform_random(14_000_000, 4)
+    IRP, JA, AS = A.IRP.copy(), A.JA.copy(), A.AS.copy()
+    h = sp.CsrDevice.from_host(A)
+    assert h.sell_info(build=True)["panels"] == 2                 # x = 112 MB: two panels for SpMV
+    rng = np.random.default_rng(33)
+    for k in (2, 4):
+        Xh = rng.uniform(-1, 1, (A.N, k))
+        X = torch.from_numpy(Xh).cuda()
+        Y = torch.full((A.M, k), float("nan"), dtype=torch.float64, device="cuda")
+        h.spmm(X, Y)
+        Yh = Y.cpu().numpy()
+        for j in (0, k - 1):
+            xj = np.ascontiguousarray(Xh[:, j])
+            ok, worst = O.check_tolerance(np.ascontiguousarray(Yh[:, j]), O.csr_spmv(A.M, IRP, JA, AS, xj),
+                                          O.csr_abs_bound(A.M, IRP, JA, AS, xj), TOL)
+            assert ok, (k, j, worst)
+    h.close()
+
+
 def test_handle_host_spmv(sp, O, torch):
     """spmv_b200_{csr,hll}_spmv_host on resident handles, including a generated-in-HBM stencil
     (no host copy of the matrix: the chunk plan comes from device reductions), pinned and

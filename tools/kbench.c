@@ -19,12 +19,13 @@
 #include <string.h>
 
 #include "csr.h"
+#include "cuda_timer.h"
 #include "hll.h"
 #include "spmv_b200.h"
 #include "spmv_gen.h"
 
 static int g_reps = 20, g_warmup = 3, g_flush = 0, g_quick = 0, g_profile = 0, g_cfg_from = -1;
-static int g_sell = 0;
+static int g_sell = 0, g_spmm = 0;
 static int g_panels[16] = {1, 2, 3, 4, 6, 8, 16}, g_n_panels = 7;
 static int g_chunks[16], g_n_chunks = 0, g_auto = 0;
 static int g_hots[16] = {0}, g_n_hots = 1;
@@ -157,6 +158,8 @@ int main(int argc, char **argv) {
                   g_profile = 1; /* only the headline kernels: for ncu captures */
             else if (!strcmp(argv[i], "--sell"))
                   g_sell = 1; /* SELL-P sweep: panels x sigma x warps/block, CSR and HLL source */
+            else if (!strcmp(argv[i], "--spmm"))
+                  g_spmm = 1; /* SpMM: 1 (id 2), 2 and 4 right-hand sides in one pass */
             else if (!strcmp(argv[i], "--auto"))
                   g_auto = 1; /* only what the library picks on its own: CSR id 2, HLL id 2 (ncu captures) */
             else if (!strcmp(argv[i], "--hot") && i + 1 < argc) {
@@ -232,6 +235,69 @@ int main(int argc, char **argv) {
                         run_hll(&c, hh, 2, 4, "auto");
                         spmv_b200_hll_destroy(hh);
                   }
+            }
+            spmv_b200_csr_destroy(h);
+            return 0;
+      }
+
+      if (g_spmm) {
+            /* k right-hand sides in one pass: time per pass, GFLOP/s = 2 nnz k / t, and the gain over
+             * k single-vector products */
+            spmv_b200_csr *h = spmv_b200_csr_create(A);
+            if (!h) {
+                  fprintf(stderr, "kbench: %s\n", spmv_b200_last_error());
+                  return 1;
+            }
+            run_csr(&c, h, 2, 4, "k=1 (SpMV)");
+            double ms1[64];
+            spmv_b200_csr_time(h, 2, 4, c.d_x, c.d_y, g_warmup, g_reps > 64 ? 64 : g_reps, g_flush, ms1, NULL);
+            qsort(ms1, g_reps > 64 ? 64 : g_reps, sizeof(double), cmp_d);
+            const double t1 = ms1[(g_reps > 64 ? 64 : g_reps) / 2];
+            for (int k = 2; k <= 4; k += 2) {
+                  double *dX = spmv_b200_dmalloc((size_t)A->N * k * 8), *dY = spmv_b200_dmalloc((size_t)A->M * k * 8);
+                  double *X = malloc((size_t)A->N * k * 8), *Y = malloc((size_t)A->M * k * 8);
+                  if (!dX || !dY || !X || !Y)
+                        return 1;
+                  for (long long i = 0; i < (long long)A->N * k; ++i)
+                        X[i] = (double)((i * 2654435761u) % 2001) / 1000.0 - 1.0;
+                  spmv_b200_h2d(dX, X, (size_t)A->N * k * 8, NULL);
+                  double ms[64];
+                  const int reps = g_reps > 64 ? 64 : g_reps;
+                  for (int r = -g_warmup; r < reps; ++r) {
+                        cuda_timer t;
+                        timer_init(&t);
+                        timer_start(&t, NULL);
+                        if (spmv_b200_csr_spmm(h, k, dX, dY, NULL)) {
+                              fprintf(stderr, "kbench: %s\n", spmv_b200_last_error());
+                              return 1;
+                        }
+                        const double m = timer_stop(&t, NULL);
+                        timer_destroy(&t);
+                        if (r >= 0)
+                              ms[r] = m;
+                  }
+                  qsort(ms, reps, sizeof(double), cmp_d);
+                  /* check column 0 and column k-1 against the host serial loop */
+                  spmv_b200_d2h(Y, dY, (size_t)A->M * k * 8, NULL);
+                  spmv_b200_stream_sync(NULL);
+                  double worst = 0.0;
+                  for (int col = 0; col < k; col += k - 1)
+                        for (int r = 0; r < A->M; ++r) {
+                              double ref = 0.0, sc = 0.0;
+                              for (int q = A->IRP[r]; q < A->IRP[r + 1]; ++q) {
+                                    const double p = A->AS[q] * X[(size_t)A->JA[q] * k + col];
+                                    ref += p, sc += fabs(p);
+                              }
+                              const double err = fabs(Y[(size_t)r * k + col] - ref);
+                              if (sc > 0 && err / sc > worst)
+                                    worst = err / sc;
+                        }
+                  const double med = ms[reps / 2];
+                  printf("CSR  spmm           k=%d  launches=-  min %8.4f ms  med %8.4f ms  %8.1f GFLOP/s  %.2fx the rate of %d "
+                         "SpMV passes  maxrel %.2e %s\n", k, ms[0], med, 2.0 * A->NZ * k / (med * 1e6), k * t1 / med, k,
+                         worst, worst <= 1e-12 ? "ok" : "MISMATCH");
+                  fflush(stdout);
+                  spmv_b200_dfree(dX), spmv_b200_dfree(dY), free(X), free(Y);
             }
             spmv_b200_csr_destroy(h);
             return 0;
