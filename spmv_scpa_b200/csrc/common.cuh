@@ -152,12 +152,20 @@ __device__ __forceinline__ double ld_x(const double *p, uint64_t pol) {
 template <int K>
 __device__ __forceinline__ void ld_xk(const double *X, int c, uint64_t pol, double (&v)[K]) {
       static_assert(K == 2 || K == 4, "2 or 4 right-hand sides");
-      const double *p = X + (long long)c * K;
+      // c < 0: no entry -> zeros, no load.  Predicated, not branched: the gathers of a batch must
+      // all be in flight together.
+      const double *p = X + (long long)(c < 0 ? 0 : c) * K;
 #pragma unroll
       for (int j = 0; j < K; j += 2)
-            asm("ld.global.nc.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;"
+            asm("{\n\t"
+                ".reg .pred q;\n\t"
+                "setp.ge.s32 q, %4, 0;\n\t"
+                "mov.f64 %0, 0d0000000000000000;\n\t"
+                "mov.f64 %1, 0d0000000000000000;\n\t"
+                "@q ld.global.nc.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;\n\t"
+                "}"
                 : "=d"(v[j]), "=d"(v[j + 1])
-                : "l"(p + j), "l"(pol));
+                : "l"(p + j), "l"(pol), "r"(c));
 }
 
 // --------------------------------------------------- mbarrier + bulk copy --

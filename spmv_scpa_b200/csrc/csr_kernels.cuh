@@ -574,15 +574,8 @@ __global__ void __launch_bounds__(512)
                   c[u] = ok ? ld_stream_s32(ja + kk, pol_s) : -1;
             }
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                  if (c[u] >= 0) {
-                        ld_xk<K>(X, c[u], pol_x, xv[u]);
-                  } else {
-#pragma unroll
-                        for (int k = 0; k < K; ++k)
-                              xv[u][k] = 0.0;
-                  }
-            }
+            for (int u = 0; u < U; ++u)
+                  ld_xk<K>(X, c[u], pol_x, xv[u]);
 #pragma unroll
             for (int u = 0; u < U; ++u)
 #pragma unroll
