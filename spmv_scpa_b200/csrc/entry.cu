@@ -232,11 +232,11 @@ class CopyPool {
     private:
       CopyPool() {
             const int n = copy_threads() - 1;
-            // busy-wait between pieces only while every rank of the box can keep its whole team on
-            // CPUs of its own with room left for the driver's and the collective library's threads
-            const char *lw = getenv("LOCAL_WORLD_SIZE");
-            const int ranks = lw && atoi(lw) > 0 ? atoi(lw) : 1;
-            spin_ok_ = allowed_cpus().count <= 0 || (n + 1) * ranks + 2 * (ranks - 1) <= allowed_cpus().count;
+            // Busy-wait between pieces while the team fits the CPUs this process may use (the team
+            // size is already divided by the ranks of the box, copy_threads()).  Yielding instead
+            // as soon as the ranks together fill the box measured 22 % slower at 2 ranks (C5 e2e,
+            // pageable buffers: 53.8 ms against 42.0 ms).
+            spin_ok_ = allowed_cpus().count <= 0 || n + 1 <= allowed_cpus().count;
             for (int i = 0; i < n; ++i)
                   workers_.emplace_back([this] { loop(); });
       }
