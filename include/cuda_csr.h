@@ -18,7 +18,8 @@
  *   0 csr_spmv_cuda_thread_row        one thread per row
  *   1 csr_spmv_cuda_warp_row          one warp per row, shuffle reduction
  *   2 csr_spmv_cuda_halfwarp_row      ADAPTIVE by row-length profile and gather locality:
- *                                     TMA-staged tiles (regular rows), sorted slices with
+ *                                     TMA-staged tiles (regular rows; per-warp rings for
+ *                                     rows of at most 8 entries), sorted slices with
  *                                     virtual rows (ragged rows), column panels (x > L2,
  *                                     scattered columns); sub-warp / warp / block-per-row
  *                                     bins on row ranges of cut shards
